@@ -1,0 +1,127 @@
+"""ctypes binding of libaadff.so (C ABI in include/aadff.h) + the in-tree build recipe.
+
+This is the only way the Python host layer reaches the GPU: there is no PyTorch-eager or CPU
+fallback behind it.  If the shared library is missing and cannot be built, importing this
+module raises -- loudly -- instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libaadff.so")
+HEADER = os.path.join(_REPO, "include", "aadff.h")
+
+MODE_PARITY, MODE_FAST, MODE_FP32, MODE_MIXED = 0, 1, 2, 3
+MODES = {"parity": MODE_PARITY, "fast": MODE_FAST, "fp32": MODE_FP32, "mixed": MODE_MIXED}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [HEADER]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/aadff_api.cu -> libaadff.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in _sources())
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("libaadff.so is not built and nvcc was not found; cannot build the CUDA extension")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(CSRC, "aadff_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    c_f32p = ctypes.POINTER(ctypes.c_float)
+    lib.aadff_version.restype = ctypes.c_int
+    lib.aadff_last_error.restype = ctypes.c_char_p
+    lib.aadff_launch_count.restype = ctypes.c_int64
+    lib.aadff_psfnet_create.argtypes = [ctypes.POINTER(c_f32p), ctypes.POINTER(c_f32p),
+                                        ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_void_p)]
+    lib.aadff_psfnet_destroy.argtypes = [ctypes.c_void_p]
+    lib.aadff_render_stack_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 5 + \
+                                          [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    lib.aadff_render_stack_host_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 5 + \
+                                               [ctypes.c_float, ctypes.c_float, ctypes.c_int]
+    lib.aadff_psfnet_pred_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_void_p]
+    lib.aadff_local_psf_render_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    lib.aadff_debug_umma_gemm.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3
+    lib.aadff_debug_set_desc_swap.argtypes = [ctypes.c_int]
+    for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32",
+               "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_local_psf_render_f32",
+               "aadff_debug_umma_gemm", "aadff_debug_set_desc_swap"):
+        getattr(lib, fn).restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+class AadffError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AadffError(f"libaadff error {rc}: {lib.aadff_last_error().decode()}")
+
+
+def exported_symbols():
+    """Names declared in include/aadff.h (used by the CPU test that checks the library exports them)."""
+    import re
+    with open(HEADER) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(aadff_[a-z0-9_]+)\s*\(", text)))
+
+
+class NativePSFNet:
+    """Owns an aadff_psfnet_t: the pre-packed network on one device."""
+
+    def __init__(self, weights, biases, ks: int, device_index: int):
+        import numpy as np
+        self._np = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        self._nb = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        n = len(self._np)
+        dims = [self._np[0].shape[1]] + [w.shape[0] for w in self._np]
+        c_f32p = ctypes.POINTER(ctypes.c_float)
+        wp = (c_f32p * n)(*[w.ctypes.data_as(c_f32p) for w in self._np])
+        bp = (c_f32p * n)(*[b.ctypes.data_as(c_f32p) for b in self._nb])
+        dm = (ctypes.c_int * (n + 1))(*dims)
+        self.handle = ctypes.c_void_p()
+        self.ks = ks
+        self.device_index = device_index
+        check(lib.aadff_psfnet_create(wp, bp, dm, n, ks, device_index, ctypes.byref(self.handle)))
+        self._np = self._nb = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.aadff_psfnet_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,416 @@
+// C-ABI of libaadff.so (declared in include/aadff.h): handle management, weight pre-packing,
+// launch configuration and error reporting for the sm_100a kernels in this directory.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aadff.h"
+#include "fused_tc_kernel.cuh"
+#include "gather_kernel.cuh"
+#include "mlp_fp32_kernel.cuh"
+
+using namespace aadff;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_desc_swap{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(AADFF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(const std::vector<T>& h, T** d) {
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(d), h.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return AADFF_OK;
+}
+
+// W rows [n0, n0+N) x all K -> K/32 slabs, each (hi, lo), canonical no-swizzle K-major layout:
+// half index inside a slab = (k/8) * (N*8) + n*8 + (k%8)
+void pack_group(const float* W, int out_f, int in_f, int n0, int N, std::vector<__half>& dst) {
+    for (int kc = 0; kc < in_f / TC_SLAB_K; ++kc) {
+        for (int part = 0; part < 2; ++part) {
+            const size_t base = dst.size();
+            dst.resize(base + (size_t)N * TC_SLAB_K);
+            for (int k = 0; k < TC_SLAB_K; ++k) {
+                for (int n = 0; n < N; ++n) {
+                    const int row = n0 + n, col = kc * TC_SLAB_K + k;
+                    const float w = (row < out_f) ? W[(size_t)row * in_f + col] : 0.0f;
+                    const __half hi = __float2half_rn(w);
+                    const __half v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
+                    dst[base + (size_t)(k / 8) * (N * 8) + (size_t)n * 8 + (k % 8)] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct aadff_psfnet {
+    int device = 0, ks = 0, kk = 0, n_layers = 0;
+    int num_sms = 0, smem_optin = 0;
+    // fp32 (CUDA-core) path
+    Fp32Net f32{};
+    std::vector<float*> owned;
+    // tcgen05 path
+    bool tc_ok = false;
+    std::string tc_why;
+    uint8_t* d_wpack = nullptr;
+    float* d_bias_tc = nullptr;
+    float* d_w0b0 = nullptr;
+    TcGroup groups[TC_MAX_GROUPS]{};
+    int n_groups = 0, n_hidden = 0, n_bias = 0;
+    // host-call workspace
+    cudaStream_t ws_stream = nullptr;
+    float* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+extern "C" {
+
+int aadff_version(void) { return AADFF_VERSION; }
+const char* aadff_last_error(void) { return g_err.c_str(); }
+int64_t aadff_launch_count(void) { return g_launches.load(); }
+int aadff_debug_set_desc_swap(int swap) {
+    g_desc_swap.store(swap ? 1 : 0);
+    return AADFF_OK;
+}
+
+int aadff_psfnet_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
+                        int ks, int device, aadff_psfnet_t* out) {
+    if (!weights || !biases || !dims || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (n_layers < 2 || n_layers > MAX_LAYERS) return fail(AADFF_E_INVALID, "n_layers must be in [2,16]");
+    if (ks < 1 || (ks % 2) == 0) return fail(AADFF_E_INVALID, "kernel size must be odd and positive");
+    if (dims[0] != 4 || dims[n_layers] != ks * ks)
+        return fail(AADFF_E_INVALID, "dims must start with 4 and end with ks*ks");
+    for (int l = 0; l < n_layers; ++l) {
+        if (!weights[l] || !biases[l]) return fail(AADFF_E_INVALID, "null layer pointer");
+        if (dims[l + 1] < 1 || (l + 1 < n_layers && (dims[l + 1] > 256 || dims[l + 1] % 8)))
+            return fail(AADFF_E_INVALID, "hidden widths must be multiples of 8 and <= 256");
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select CUDA device " + std::to_string(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(AADFF_E_CUDA, "libaadff is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor));
+
+    aadff_psfnet* h = new aadff_psfnet();
+    h->device = device;
+    h->ks = ks;
+    h->kk = ks * ks;
+    h->n_layers = n_layers;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+    // ---- fp32 path: W^T [K][npad], bias [npad]
+    h->f32.n_layers = n_layers;
+    h->f32.kk = h->kk;
+    for (int l = 0; l < n_layers; ++l) {
+        const int K = dims[l], Nf = dims[l + 1], npad = (Nf + 7) / 8 * 8;
+        std::vector<float> wt((size_t)K * npad, 0.f), b(npad, 0.f);
+        for (int n = 0; n < Nf; ++n) {
+            b[n] = biases[l][n];
+            for (int k = 0; k < K; ++k) wt[(size_t)k * npad + n] = weights[l][(size_t)n * K + k];
+        }
+        float *dw = nullptr, *db = nullptr;
+        int rc = upload(wt, &dw);
+        if (rc) { aadff_psfnet_destroy(h); return rc; }
+        h->owned.push_back(dw);
+        rc = upload(b, &db);
+        if (rc) { aadff_psfnet_destroy(h); return rc; }
+        h->owned.push_back(db);
+        h->f32.wt[l] = dw;
+        h->f32.bias[l] = db;
+        h->f32.k[l] = K;
+        h->f32.npad[l] = npad;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
+
+    // ---- tcgen05 path: needs the PSFNet architecture 4 -> 64 -> 256 -> 256 x n -> ks^2
+    h->tc_ok = true;
+    if (n_layers < 3 || dims[1] != 64) { h->tc_ok = false; h->tc_why = "first hidden width must be 64"; }
+    for (int l = 2; l < n_layers && h->tc_ok; ++l)
+        if (dims[l] != TC_HID) { h->tc_ok = false; h->tc_why = "hidden width must be 256"; }
+    if (ks > TC_MAX_KS) { h->tc_ok = false; h->tc_why = "kernel size > 31"; }
+    const int nh_pad = (h->kk + 15) / 16 * 16;
+    const int n_head_blocks = (nh_pad + 255) / 256;
+    if (h->tc_ok && (n_layers - 2) + n_head_blocks > TC_MAX_GROUPS) { h->tc_ok = false; h->tc_why = "too many layers"; }
+    if (h->tc_ok) {
+        std::vector<__half> pack;
+        std::vector<float> bias_tc;
+        int gi = 0;
+        for (int l = 1; l < n_layers - 1; ++l, ++gi) {      // L1 .. L(n-2): hidden MMA layers
+            TcGroup& g = h->groups[gi];
+            g.w_off = (uint32_t)(pack.size() * sizeof(__half));
+            g.K = (uint16_t)dims[l];
+            g.N = TC_HID;
+            g.terms = 3;
+            g.bias_off = (uint16_t)bias_tc.size();
+            g.new_a = 1;
+            g.tap0 = 0;
+            pack_group(weights[l], dims[l + 1], dims[l], 0, TC_HID, pack);
+            bias_tc.insert(bias_tc.end(), biases[l], biases[l] + TC_HID);
+        }
+        h->n_hidden = gi;
+        const int L = n_layers - 1;
+        const int head_bias0 = (int)bias_tc.size();
+        bias_tc.resize(head_bias0 + nh_pad, 0.f);
+        for (int n = 0; n < h->kk; ++n) bias_tc[head_bias0 + n] = biases[L][n];
+        for (int b = 0; b < n_head_blocks; ++b, ++gi) {
+            TcGroup& g = h->groups[gi];
+            const int N = std::min(256, nh_pad - 256 * b);
+            g.w_off = (uint32_t)(pack.size() * sizeof(__half));
+            g.K = TC_HID;
+            g.N = (uint16_t)N;
+            g.terms = 3;
+            g.bias_off = (uint16_t)(head_bias0 + 256 * b);
+            g.new_a = (b == 0);
+            g.tap0 = (uint16_t)(256 * b);
+            pack_group(weights[L], h->kk, TC_HID, 256 * b, N, pack);
+        }
+        h->n_groups = gi;
+        h->n_bias = (int)bias_tc.size();
+        std::vector<float> w0b0(320);
+        std::memcpy(w0b0.data(), weights[0], 256 * sizeof(float));
+        std::memcpy(w0b0.data() + 256, biases[0], 64 * sizeof(float));
+        __half* dp = nullptr;
+        int rc = upload(pack, &dp);
+        if (rc) { aadff_psfnet_destroy(h); return rc; }
+        h->d_wpack = reinterpret_cast<uint8_t*>(dp);
+        rc = upload(bias_tc, &h->d_bias_tc);
+        if (rc) { aadff_psfnet_destroy(h); return rc; }
+        rc = upload(w0b0, &h->d_w0b0);
+        if (rc) { aadff_psfnet_destroy(h); return rc; }
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      h->smem_optin));
+    }
+    *out = h;
+    return AADFF_OK;
+}
+
+int aadff_psfnet_destroy(aadff_psfnet_t h) {
+    if (!h) return AADFF_OK;
+    DeviceGuard guard(h->device);
+    for (float* p : h->owned) cudaFree(p);
+    cudaFree(h->d_wpack);
+    cudaFree(h->d_bias_tc);
+    cudaFree(h->d_w0b0);
+    cudaFree(h->ws);
+    if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
+    delete h;
+    return AADFF_OK;
+}
+
+static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st) {
+    if (!h->tc_ok) return fail(AADFF_E_UNSUPPORTED, "tensor-core path unavailable: " + h->tc_why + " (use AADFF_MODE_FP32)");
+    TcParams P{};
+    P.ra = ra;
+    P.wpack = h->d_wpack;
+    P.bias = h->d_bias_tc;
+    P.w0b0 = h->d_w0b0;
+    P.n_groups = h->n_groups;
+    P.n_hidden = h->n_hidden;
+    P.n_bias = h->n_bias;
+    P.kk = h->kk;
+    for (int i = 0; i < h->n_groups; ++i) {
+        P.g[i] = h->groups[i];
+        P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1 : (mode == AADFF_MODE_MIXED && i >= 3) ? 1 : 3;
+    }
+    P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
+    P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
+    P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
+    P.swap_lbo_sbo = (uint32_t)g_desc_swap.load();
+    // shared-memory carve-up
+    const uint32_t halo_bytes = (uint32_t)ra.C * (TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 4;
+    const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + 256;
+    int stages = TC_MAX_STAGES;
+    while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;
+    if (stages < 2) return fail(AADFF_E_UNSUPPORTED, "shared memory budget exceeded for this kernel size / channel count");
+    P.n_stages = stages;
+    P.off_stage = 2 * TC_A_PART_BYTES;
+    P.off_bias = P.off_stage + stages * TC_STAGE_BYTES;
+    P.off_w0 = P.off_bias + (uint32_t)h->n_bias * 4;
+    P.off_halo = P.off_w0 + 320 * 4;
+    P.off_red = P.off_halo + halo_bytes;
+    P.off_bar = P.off_red + TC_M * 5 * 4;
+    const uint32_t smem = P.off_bar + 256;
+    const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
+    fused_psfnet_render_kernel<<<grid, TC_NT, smem, st>>>(P);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, float* out,
+                           const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                           float d_max, int mode, void* stream) {
+    if (!h || !img || !depth || !foc || !out || !out_strides) return fail(AADFF_E_INVALID, "null argument");
+    if (N < 0 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (mode < 0 || mode > 3) return fail(AADFF_E_INVALID, "unknown mode");
+    if (d_max == d_min) return fail(AADFF_E_INVALID, "d_max == d_min");
+    if (N == 0) return AADFF_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RenderArgs ra{};
+    ra.img = img; ra.depth = depth; ra.foc = foc; ra.out = out;
+    ra.os_n = out_strides[0]; ra.os_c = out_strides[1]; ra.os_s = out_strides[2];
+    ra.os_h = out_strides[3]; ra.os_w = out_strides[4];
+    ra.N = N; ra.S = S; ra.H = H; ra.W = W; ra.ks = h->ks; ra.Ctot = C;
+    ra.d_min = d_min;
+    ra.d_range = d_max - d_min;
+    ra.step_x = (W > 1) ? (1.0f - (-1.0f)) / (float)(W - 1) : 0.f;
+    ra.step_y = (H > 1) ? (-1.0f - 1.0f) / (float)(H - 1) : 0.f;
+    for (int c0 = 0; c0 < C; c0 += 4) {          // PSFs are shared by all channels; > 4 channels -> several passes
+        ra.c0 = c0;
+        ra.C = std::min(4, C - c0);
+        if (mode == AADFF_MODE_FP32) {
+            const long long M = (long long)N * S * H * W;
+            const int grid = (int)std::min<long long>((M + F32_TP - 1) / F32_TP, (long long)h->num_sms * 8);
+            mlp_fp32_kernel<true><<<grid, F32_NT, F32_SMEM, st>>>(h->f32, ra, nullptr, nullptr, M);
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            int rc = launch_tc(h, ra, mode, st);
+            if (rc) return rc;
+        }
+    }
+    return AADFF_OK;
+}
+
+int aadff_render_stack_host_f32(aadff_psfnet_t h, const float* img, const float* depth, const float* foc,
+                                float* out, int N, int C, int S, int H, int W, float d_min, float d_max, int mode) {
+    if (!h || !img || !depth || !foc || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (N < 1 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    const size_t n_img = (size_t)N * C * H * W, n_dep = (size_t)N * H * W, n_foc = (size_t)N * S;
+    const size_t n_out = n_img * S;
+    auto up = [](size_t n) { return (n + 63) / 64 * 64; };
+    const size_t need = (up(n_img) + up(n_dep) + up(n_foc) + up(n_out)) * sizeof(float);
+    if (!h->ws_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->ws_stream, cudaStreamNonBlocking));
+    if (need > h->ws_bytes) {
+        if (h->ws) CUDA_TRY(cudaFree(h->ws));
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->ws), need));
+        h->ws_bytes = need;
+    }
+    float* d_img = h->ws;
+    float* d_dep = d_img + up(n_img);
+    float* d_foc = d_dep + up(n_dep);
+    float* d_out = d_foc + up(n_foc);
+    cudaStream_t st = h->ws_stream;
+    CUDA_TRY(cudaMemcpyAsync(d_img, img, n_img * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_dep, depth, n_dep * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_foc, foc, n_foc * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int64_t strides[5] = {(int64_t)C * S * H * W, (int64_t)S * H * W, (int64_t)H * W, W, 1};
+    int rc = aadff_render_stack_f32(h, d_img, d_dep, d_foc, d_out, strides, N, C, S, H, W, d_min, d_max, mode, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return AADFF_OK;
+}
+
+int aadff_psfnet_pred_f32(aadff_psfnet_t h, const float* inp, float* psf, int64_t M, void* stream) {
+    if (!h || !inp || !psf) return fail(AADFF_E_INVALID, "null argument");
+    if (M < 0) return fail(AADFF_E_INVALID, "negative M");
+    if (M == 0) return AADFF_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    RenderArgs ra{};
+    ra.ks = h->ks;
+    const int grid = (int)std::min<long long>((M + F32_TP - 1) / F32_TP, (long long)h->num_sms * 8);
+    mlp_fp32_kernel<false><<<grid, F32_NT, F32_SMEM, static_cast<cudaStream_t>(stream)>>>(h->f32, ra, inp, psf, M);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, int N, int C, int H, int W, int ks,
+                               void* stream) {
+    if (!img || !psf || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (N < 0 || C < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (ks < 1 || (ks % 2) == 0) return fail(AADFF_E_INVALID, "kernel size must be odd and positive");
+    if (N == 0) return AADFF_OK;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static std::atomic<bool> attr_set{false};
+    const int smem = GATHER_WARPS * 32 * (GATHER_TT + 1) * (int)sizeof(float);
+    if (!attr_set.exchange(true))
+        CUDA_TRY(cudaFuncSetAttribute(local_psf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long items = (long long)N * H * ((W + 31) / 32);
+    const int grid = (int)std::min<long long>((items + GATHER_WARPS - 1) / GATHER_WARPS, (long long)sms * 3);
+    for (int c0 = 0; c0 < C; c0 += GATHER_MAXC) {
+        local_psf_render_kernel<<<grid, GATHER_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            img, psf, out, N, C, H, W, ks, c0, std::min(GATHER_MAXC, C - c0));
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return AADFF_OK;
+}
+
+int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N, int device) {
+    if (!A || !B || !D) return fail(AADFF_E_INVALID, "null argument");
+    if (K < 32 || K > 256 || K % 32 || N < 16 || N > 256 || N % 16) return fail(AADFF_E_INVALID, "bad K/N");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    std::vector<__half> pack_all, pack_hi;
+    pack_group(B, N, K, 0, N, pack_all);                 // (hi, lo) per slab; keep the hi slabs only
+    for (int kc = 0; kc < K / TC_SLAB_K; ++kc)
+        pack_hi.insert(pack_hi.end(), pack_all.begin() + (size_t)(2 * kc) * N * TC_SLAB_K,
+                       pack_all.begin() + (size_t)(2 * kc + 1) * N * TC_SLAB_K);
+    float *dA = nullptr, *dD = nullptr;
+    __half* dB = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dA), (size_t)128 * K * 4));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dD), (size_t)128 * N * 4));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dB), pack_hi.size() * 2));
+    CUDA_TRY(cudaMemcpy(dA, A, (size_t)128 * K * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dB, pack_hi.data(), pack_hi.size() * 2, cudaMemcpyHostToDevice));
+    const int smem = TC_A_PART_BYTES + 131072 + 64;
+    CUDA_TRY(cudaFuncSetAttribute(debug_umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    debug_umma_gemm_kernel<<<1, 128, smem>>>(dA, reinterpret_cast<const uint8_t*>(dB), dD, K, N,
+                                             (uint32_t)g_desc_swap.load());
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(D, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return AADFF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// Fused PSFNet + per-pixel PSF render for sm_100a (tcgen05 / TMEM / bulk-async copies).
+//
+// Replaces, for one focal stack, the reference's
+//   PSFNet.render  (deeplens/psfnet.py:393-441)  -> MLP.forward (deeplens/psfnet_arch.py:24-47)
+//   -> local_psf_render (deeplens/render_psf.py:76-107), called S times and stacked
+//   (2_aber_aware_dff_aif.py:108-114).
+// The per-pixel k x k PSFs exist only in tensor memory and registers.
+//
+// Work unit: a tile of 8 x 16 = 128 output pixels of one (image, slice); MMA M = 128, one
+// TMEM lane per pixel.  A persistent CTA (one per SM) walks tiles round-robin.
+//
+//   warp 0      weight producer: streams pre-packed fp16 weight slabs L2 -> smem ring
+//               (cp.async.bulk + mbarrier complete_tx), also owns TMEM alloc/dealloc
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::f16, M128 x N<=256 x K16),
+//               accumulators ping-pong between TMEM columns [0,256) and [256,512)
+//   warps 2-9   epilogue/compute (256 threads, two warps per TMEM lane quadrant):
+//               layer 0 (4->64) in fp32 FFMA, per-layer epilogue (TMEM -> +bias -> ReLU ->
+//               fp16 hi/lo split -> K-major smem operand for the next layer), and the head
+//               epilogue (sigmoid -> k x k gather from the smem halo tile -> normalise -> store)
+//
+// Precision: fp16 operands cannot hold the activations/weights to the 1e-4 image tolerance
+// (SURVEY.md 7.3), so in parity mode every product is evaluated as
+//   A*W ~= Ah*Wh + Al*Wh + Ah*Wl   (Ah = fp16(A), Al = fp16(A - Ah), same for W)
+// with fp32 accumulation in TMEM: three tcgen05.mma per K-step.  "terms" is per layer, so
+// fast (1-term) and mixed modes are the same kernel.
+//
+// Intra-tile pipelining: the epilogue of layer l hands its output to the MMA warp in 64-column
+// chunks (a_ready[j]); the MMAs of layer l+1 for K-chunk j start as soon as chunk j is in smem and
+// write the *other* accumulator, so the tensor pipe idles only for the first chunk of each epilogue.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include "ptx_sm100.cuh"
+#include "render_args.h"
+
+namespace aadff {
+
+constexpr int TC_TILE_H = 8;
+constexpr int TC_TILE_W = 16;
+constexpr int TC_M = TC_TILE_H * TC_TILE_W;           // 128 pixels = MMA M
+constexpr int TC_HALO_PITCH = 48;                     // floats; 48 % 32 == 16 -> 2 tile rows/warp conflict-free
+constexpr int TC_HID = 256;
+constexpr int TC_SLAB_K = 32;                         // K columns per weight slab (2 MMA K-steps)
+constexpr int TC_STAGE_BYTES = TC_HID * TC_SLAB_K * 2;  // 16 KB
+constexpr int TC_A_PART_BYTES = TC_M * TC_HID * 2;    // 64 KB: one fp16 [128 x 256] operand
+constexpr int TC_A_LBO = TC_M * 16;                   // 2048 B between K-adjacent core matrices of A
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_NT = 64 + TC_EPI_THREADS;            // 320 threads
+constexpr int TC_MAX_GROUPS = 16;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_KS = 31;
+constexpr int TC_MAX_C = 4;
+
+struct TcGroup {            // one accumulation group: one layer, or one <=256-column block of the head
+    uint32_t w_off;         // byte offset of its first slab in the packed weights
+    uint16_t K;             // 64 or 256
+    uint16_t N;             // MMA N: multiple of 16, <= 256
+    uint16_t terms;         // 3 = hi*hi + lo*hi + hi*lo, 1 = hi*hi only
+    uint16_t bias_off;      // float offset into the bias table
+    uint16_t new_a;         // 1: consumes a freshly produced A operand (wait a_ready), 0: reuses it
+    uint16_t tap0;          // head blocks: first tap (output feature) of the block
+};
+
+struct TcParams {
+    RenderArgs ra;
+    const uint8_t* wpack;   // fp16 slabs, consumption order
+    const float* bias;      // L1..L9 biases then the padded head bias
+    const float* w0b0;      // W0 [64][4] then b0 [64]
+    TcGroup g[TC_MAX_GROUPS];
+    int n_groups, n_hidden; // n_hidden = 9 (L1..L9); the rest are head blocks
+    int n_bias, n_stages, kk;
+    int tiles_x, tiles_y;
+    long long n_tiles;
+    // shared-memory byte offsets
+    uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar;
+    uint32_t swap_lbo_sbo;  // debug: descriptor field convention probe
+};
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t swap) {
+    return swap ? umma_smem_desc(addr, sbo, lbo) : umma_smem_desc(addr, lbo, sbo);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// v[8] (fp32) -> fp16 hi (and lo = fp16(v - hi)) -> one 16-byte row of a K-major core matrix
+__device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_hi, uint32_t addr_lo, bool need_lo) {
+    uint32_t h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[u] = pack_half2(v[2 * u], v[2 * u + 1]);
+    st_shared_v4(addr_hi, h[0], h[1], h[2], h[3]);
+    if (need_lo) {
+        uint32_t l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 f = __half22float2(*reinterpret_cast<__half2*>(&h[u]));
+            l[u] = pack_half2(v[2 * u] - f.x, v[2 * u + 1] - f.y);
+        }
+        st_shared_v4(addr_lo, l[0], l[1], l[2], l[3]);
+    }
+}
+
+__global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const RenderArgs& ra = P.ra;
+
+    const uint32_t a_hi = sbase, a_lo = sbase + TC_A_PART_BYTES;
+    const uint32_t stage0 = sbase + P.off_stage;
+    float* s_bias = reinterpret_cast<float*>(smem + P.off_bias);
+    float* s_w0 = reinterpret_cast<float*>(smem + P.off_w0);
+    float* s_halo = reinterpret_cast<float*>(smem + P.off_halo);
+    float* s_red = reinterpret_cast<float*>(smem + P.off_red);
+    const uint32_t bar0 = sbase + P.off_bar;
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+    auto bar_aready = [&](int j) { return bar0 + 8u * (2 * TC_MAX_STAGES + j); };
+    auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 4 + b); };
+    auto bar_accfree = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 6 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 8));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int j = 0; j < 4; ++j) mbar_init(bar_aready(j), TC_EPI_WARPS);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < P.n_bias; i += TC_NT) s_bias[i] = __ldg(P.bias + i);
+    for (int i = threadIdx.x; i < 320; i += TC_NT) s_w0[i] = __ldg(P.w0b0 + i);
+    if (warp == 0) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================================================== weight producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int gi = 0; gi < P.n_groups; ++gi) {
+                    const TcGroup g = P.g[gi];
+                    const uint32_t bytes = (uint32_t)g.N * (TC_SLAB_K * 2);
+                    const int nparts = (g.terms == 3) ? 2 : 1;
+                    const uint8_t* src = P.wpack + g.w_off;
+                    for (int kc = 0; kc < g.K / TC_SLAB_K; ++kc) {
+                        for (int part = 0; part < nparts; ++part) {
+                            mbar_wait(bar_empty(stage), phase ^ 1);
+                            mbar_arrive_expect_tx(bar_full(stage), bytes);
+                            bulk_g2s(stage0 + stage * TC_STAGE_BYTES, src + (size_t)(kc * 2 + part) * bytes, bytes,
+                                     bar_full(stage));
+                            if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t fphase = 0, aphase = 0, frphase = 0;     // bit j / bit b = parity to wait for next
+            unsigned long long gcount = 0;
+            const uint32_t sw = P.swap_lbo_sbo;
+            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int gi = 0; gi < P.n_groups; ++gi) {
+                    const TcGroup g = P.g[gi];
+                    const int buf = (int)(gcount & 1);
+                    if (gcount >= 2) {           // the epilogue must have drained group gcount-2
+                        mbar_wait(bar_accfree(buf), (frphase >> buf) & 1);
+                        frphase ^= 1u << buf;
+                    }
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + buf * 256;
+                    const uint32_t idesc = umma_idesc_f16_f32(TC_M, g.N);
+                    const uint32_t lbo_b = (uint32_t)g.N * 16;
+                    uint32_t acc = 0;
+                    for (int kc = 0; kc < g.K / TC_SLAB_K; ++kc) {
+                        if (g.new_a && (kc & 1) == 0) {
+                            const int j = kc >> 1;
+                            mbar_wait(bar_aready(j), (aphase >> j) & 1);
+                            aphase ^= 1u << j;
+                            tc_fence_after_sync();
+                        }
+                        // ---- hi weight slab: Ah*Wh (+ Al*Wh)
+                        mbar_wait(bar_full(stage), fphase);
+                        tc_fence_after_sync();
+                        uint32_t b_addr = stage0 + stage * TC_STAGE_BYTES;
+#pragma unroll
+                        for (int k2 = 0; k2 < 2; ++k2) {
+                            const uint32_t koff = (uint32_t)(kc * 2 + k2) * (2 * TC_A_LBO);
+                            umma_f16_ss(d_tmem, tc_desc(a_hi + koff, TC_A_LBO, 128, sw),
+                                        tc_desc(b_addr + k2 * 2 * lbo_b, lbo_b, 128, sw), idesc, acc);
+                            acc = 1;
+                        }
+                        if (g.terms == 3) {
+#pragma unroll
+                            for (int k2 = 0; k2 < 2; ++k2) {
+                                const uint32_t koff = (uint32_t)(kc * 2 + k2) * (2 * TC_A_LBO);
+                                umma_f16_ss(d_tmem, tc_desc(a_lo + koff, TC_A_LBO, 128, sw),
+                                            tc_desc(b_addr + k2 * 2 * lbo_b, lbo_b, 128, sw), idesc, 1);
+                            }
+                        }
+                        umma_commit(bar_empty(stage));
+                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                        if (g.terms == 3) {
+                            // ---- lo weight slab: Ah*Wl
+                            mbar_wait(bar_full(stage), fphase);
+                            tc_fence_after_sync();
+                            b_addr = stage0 + stage * TC_STAGE_BYTES;
+#pragma unroll
+                            for (int k2 = 0; k2 < 2; ++k2) {
+                                const uint32_t koff = (uint32_t)(kc * 2 + k2) * (2 * TC_A_LBO);
+                                umma_f16_ss(d_tmem, tc_desc(a_hi + koff, TC_A_LBO, 128, sw),
+                                            tc_desc(b_addr + k2 * 2 * lbo_b, lbo_b, 128, sw), idesc, 1);
+                            }
+                            umma_commit(bar_empty(stage));
+                            if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                        }
+                    }
+                    umma_commit(bar_accfull(buf));
+                    ++gcount;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================================================== epilogue / compute warps
+        const int e = warp - 2;                 // 0..7
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int hh = e >> 2;                  // which half of the columns this warp takes
+        const int et = e * 32 + lane;           // 0..255
+        const int row = q * 32 + lane;          // pixel within the tile = TMEM lane = MMA row
+        const int ty = row >> 4, tx = row & 15;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int ks = ra.ks, r = (ks - 1) / 2, kk = P.kk;
+        const int HH = TC_TILE_H + ks - 1, HW = TC_TILE_W + ks - 1;
+        const int plane = HH * TC_HALO_PITCH;
+        const int tiles_xy = P.tiles_x * P.tiles_y;
+        const uint32_t a_row = (uint32_t)row * 16;
+        uint32_t afphase = 0;
+        unsigned long long gcount = 0;
+        const float LOG2E = 1.4426950408889634f;
+
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            const int txy = (int)(tile % tiles_xy);
+            const long long ns = tile / tiles_xy;
+            const int s = (int)(ns % ra.S), n = (int)(ns / ra.S);
+            const int h0 = (txy / P.tiles_x) * TC_TILE_H, w0 = (txy % P.tiles_x) * TC_TILE_W;
+            const int h = h0 + ty, w = w0 + tx;
+            const bool valid = (h < ra.H) && (w < ra.W);
+
+            named_bar_sync(1, TC_EPI_THREADS);       // previous tile's gather is done with halo/red
+            // ---- halo tile, replicate-clamped (render_psf.py:96), C planes of HH x 48
+            {
+                const float* img_n = ra.img + ((long long)n * ra.Ctot + ra.c0) * ra.H * ra.W;
+                const int per = HH * HW;
+                for (int idx = et; idx < ra.C * per; idx += TC_EPI_THREADS) {
+                    const int c = idx / per, rem = idx - c * per;
+                    const int yy = rem / HW, xx = rem - yy * HW;
+                    const int gy = min(max(h0 + yy - r, 0), ra.H - 1);
+                    const int gx = min(max(w0 + xx - r, 0), ra.W - 1);
+                    s_halo[c * plane + yy * TC_HALO_PITCH + xx] = __ldg(img_n + ((long long)c * ra.H + gy) * ra.W + gx);
+                }
+            }
+            // ---- layer 0 (4 -> 64) in fp32: this thread computes features [32*hh, 32*hh+32) of its pixel
+            {
+                const int hc = min(h, ra.H - 1), wc = min(w, ra.W - 1);
+                const float x = coord_x(wc, ra.W, ra.step_x);
+                const float y = coord_y(hc, ra.H, ra.step_y);
+                const float z = depth_to_z(__ldg(ra.depth + ((long long)n * ra.H + hc) * ra.W + wc), ra.d_min, ra.d_range);
+                const float fz = depth_to_z(__ldg(ra.foc + (long long)n * ra.S + s), ra.d_min, ra.d_range);
+                const bool need_lo = P.g[0].terms == 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int f = hh * 32 + i * 8 + u;
+                        const float4 wv = *reinterpret_cast<const float4*>(s_w0 + f * 4);
+                        float a = s_w0[256 + f];
+                        a = fmaf(wv.x, x, a); a = fmaf(wv.y, y, a); a = fmaf(wv.z, z, a); a = fmaf(wv.w, fz, a);
+                        v[u] = fmaxf(a, 0.f);
+                    }
+                    const uint32_t off = (uint32_t)(hh * 4 + i) * TC_A_LBO + a_row;
+                    store_split8(v, a_hi + off, a_lo + off, need_lo);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_aready(0));
+            }
+            named_bar_sync(1, TC_EPI_THREADS);       // halo tile complete
+
+            // ---- hidden layers L1..L9: accumulator -> bias, ReLU, split -> A operand of the next layer
+            for (int gi = 0; gi < P.n_hidden; ++gi) {
+                const int buf = (int)(gcount & 1);
+                mbar_wait(bar_accfull(buf), (afphase >> buf) & 1);
+                afphase ^= 1u << buf;
+                tc_fence_after_sync();
+                const bool need_lo = P.g[gi + 1].terms == 3;
+                const float* bias = s_bias + P.g[gi].bias_off;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int col = j * 64 + hh * 32;
+                    uint32_t rr[32];
+                    tmem_ld32(t_lane + buf * 256 + col, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias + col + i * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias + col + i * 8 + 4);
+                        float v[8];
+                        v[0] = fmaxf(__uint_as_float(rr[i * 8 + 0]) + b0.x, 0.f);
+                        v[1] = fmaxf(__uint_as_float(rr[i * 8 + 1]) + b0.y, 0.f);
+                        v[2] = fmaxf(__uint_as_float(rr[i * 8 + 2]) + b0.z, 0.f);
+                        v[3] = fmaxf(__uint_as_float(rr[i * 8 + 3]) + b0.w, 0.f);
+                        v[4] = fmaxf(__uint_as_float(rr[i * 8 + 4]) + b1.x, 0.f);
+                        v[5] = fmaxf(__uint_as_float(rr[i * 8 + 5]) + b1.y, 0.f);
+                        v[6] = fmaxf(__uint_as_float(rr[i * 8 + 6]) + b1.z, 0.f);
+                        v[7] = fmaxf(__uint_as_float(rr[i * 8 + 7]) + b1.w, 0.f);
+                        const uint32_t off = (uint32_t)(col / 8 + i) * TC_A_LBO + a_row;
+                        store_split8(v, a_hi + off, a_lo + off, need_lo);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_aready(j));
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accfree(buf));
+                ++gcount;
+            }
+
+            // ---- head blocks: sigmoid, gather from the halo tile (render_psf.py:103-105)
+            float ssum = 0.f, cacc[TC_MAX_C] = {0.f, 0.f, 0.f, 0.f};
+            const float* hbase = s_halo + ty * TC_HALO_PITCH + tx;
+            for (int gi = P.n_hidden; gi < P.n_groups; ++gi) {
+                const int buf = (int)(gcount & 1);
+                mbar_wait(bar_accfull(buf), (afphase >> buf) & 1);
+                afphase ^= 1u << buf;
+                tc_fence_after_sync();
+                const int gN = P.g[gi].N, gtap0 = P.g[gi].tap0;
+                const float* bias = s_bias + P.g[gi].bias_off;
+#pragma unroll 1
+                for (int c32 = hh * 32; c32 < gN; c32 += 64) {
+                    uint32_t rr[32];
+                    tmem_ld32(t_lane + buf * 256 + c32, rr);
+                    tmem_ld_wait();
+                    const int tap_first = gtap0 + c32;
+                    int i = tap_first / ks, j = tap_first - i * ks;
+                    int off = i * TC_HALO_PITCH + j;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        if (tap_first + u < kk) {          // warp-uniform: padding columns are skipped
+                            const float xlogit = __uint_as_float(rr[u]) + bias[c32 + u];
+                            const float sg = rcp_approx(1.0f + ex2_approx(-xlogit * LOG2E));
+                            ssum += sg;
+#pragma unroll
+                            for (int c = 0; c < TC_MAX_C; ++c)
+                                if (c < ra.C) cacc[c] = fmaf(sg, hbase[c * plane + off], cacc[c]);
+                        }
+                        ++off;
+                        if (++j == ks) { j = 0; off += TC_HALO_PITCH - ks; }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accfree(buf));
+                ++gcount;
+            }
+            // ---- combine the two column-halves of each pixel, normalise (F.normalize p=1), store
+            if (hh == 1) {
+                s_red[row * 5 + 0] = ssum;
+#pragma unroll
+                for (int c = 0; c < TC_MAX_C; ++c) s_red[row * 5 + 1 + c] = cacc[c];
+            }
+            named_bar_sync(2 + q, 64);
+            if (hh == 0 && valid) {
+                const float inv = 1.0f / fmaxf(ssum + s_red[row * 5], 1e-12f);
+                float* o = ra.out + n * ra.os_n + ra.c0 * ra.os_c + s * ra.os_s + h * ra.os_h + w * ra.os_w;
+#pragma unroll
+                for (int c = 0; c < TC_MAX_C; ++c)
+                    if (c < ra.C) o[c * ra.os_c] = (cacc[c] + s_red[row * 5 + 1 + c]) * inv;
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Debug / unit-test kernel: D[128 x N] = A[128 x K] * B[N x K]^T with the exact operand
+// layouts, descriptors and TMEM read-back used above (single CTA, single MMA term).
+// bpack is B pre-packed by the host packer as K/32 slabs of [N x 32].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+debug_umma_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ bpack, float* __restrict__ D,
+                       int K, int N, uint32_t swap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_hi = sbase;                               // [K/8][128][8] fp16
+    const uint32_t b_sm = sbase + TC_A_PART_BYTES;             // K/32 slabs of N*64 bytes
+    const uint32_t bar = sbase + TC_A_PART_BYTES + 131072;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + TC_A_PART_BYTES + 131072 + 16);
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(slot)));
+    // A -> fp16 K-major canonical layout
+    const int row = threadIdx.x;
+    for (int kg = 0; kg < K / 8; ++kg) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = A[(size_t)row * K + kg * 8 + u];
+        store_split8(v, a_hi + kg * TC_A_LBO + row * 16, 0, false);
+    }
+    const int bbytes = (K / 32) * N * 64;
+    for (int i = threadIdx.x * 16; i < bbytes; i += 128 * 16)
+        *reinterpret_cast<uint4*>(smem + TC_A_PART_BYTES + i) = *reinterpret_cast<const uint4*>(bpack + i);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = umma_idesc_f16_f32(128, N);
+        const uint32_t lbo_b = (uint32_t)N * 16;
+        for (int ks16 = 0; ks16 < K / 16; ++ks16) {
+            const uint32_t slab = b_sm + (ks16 / 2) * (N * 64);
+            umma_f16_ss(tmem_base, tc_desc(a_hi + ks16 * 2 * TC_A_LBO, TC_A_LBO, 128, swap),
+                        tc_desc(slab + (ks16 & 1) * 2 * lbo_b, lbo_b, 128, swap), idesc, ks16 > 0);
+        }
+        umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, rr);
+        tmem_ld_wait();
+        for (int u = 0; u < 32; ++u)
+            if (c0 + u < N) D[(size_t)row * N + c0 + u] = __uint_as_float(rr[u]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace aadff

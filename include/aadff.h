@@ -1,0 +1,92 @@
+/* aadff.h -- C ABI of libaadff.so: B200 (sm_100a) aberrated focal-stack synthesis.
+ *
+ * The reference (singer-yang/Aberration-Aware-Depth-from-Focus) is pure Python/PyTorch and has
+ * no FFI of its own; this header is the boundary a maintainer binds underneath the unchanged
+ * Python surface.  Each entry point names the reference interface it replaces (file:line
+ * relative to the reference repository).  See INTEGRATION.md for the ctypes binding.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); every function returns
+ * 0 on success or a negative AADFF_E_* code, with a human-readable message available from
+ * aadff_last_error() (thread-local).  Device-pointer entry points are asynchronous and
+ * stream-ordered on `stream` (a CUstream / cudaStream_t passed as void*; NULL = legacy default
+ * stream); they never allocate, never synchronise and never touch the inputs.  All tensors are
+ * fp32 and dense ("contiguous") unless strides are given.  There is no CPU fallback: on a
+ * machine without an sm_100 device every compute call fails with AADFF_E_CUDA.
+ */
+#ifndef AADFF_H_
+#define AADFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AADFF_VERSION 100
+
+#define AADFF_OK 0
+#define AADFF_E_INVALID (-1)      /* bad argument (null pointer, shape, kernel size ...) */
+#define AADFF_E_CUDA (-2)         /* CUDA runtime error, message has the cudaError string */
+#define AADFF_E_UNSUPPORTED (-3)  /* valid request this build cannot serve on the chosen mode */
+
+/* Arithmetic of the PSFNet MLP (deeplens/psfnet_arch.py:24-47) inside the fused kernel.      */
+#define AADFF_MODE_PARITY 0 /* tcgen05, fp16 hi/lo split operands, 3 MMA terms: <=1e-4 vs fp32 reference */
+#define AADFF_MODE_FAST 1   /* tcgen05, single fp16 term: max-abs <= 3e-2 on noise images, see DESIGN.md */
+#define AADFF_MODE_FP32 2   /* CUDA-core fp32 FFMA, operation-for-operation with the reference          */
+#define AADFF_MODE_MIXED 3  /* tcgen05, 3 terms for the first three MMA layers, 1 term afterwards        */
+
+typedef struct aadff_psfnet* aadff_psfnet_t;
+
+int aadff_version(void);
+const char* aadff_last_error(void);
+
+/* Replaces PSFNet.init_net + PSFNet.load_net (deeplens/psfnet.py:44-76): takes the state_dict
+ * of MLP(4, ks*ks, 256, hidden_layers) as HOST pointers -- weights[l] is `net.{2l}.weight`
+ * ([dims[l+1], dims[l]] row-major), biases[l] is `net.{2l}.bias` -- and uploads them to
+ * `device` pre-packed for the kernels (fp16 hi/lo K-major slabs for tcgen05, W^T for fp32).
+ * dims has n_layers+1 entries and must be {4, 64, 256, ..., 256, ks*ks}.                       */
+int aadff_psfnet_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
+                        int ks, int device, aadff_psfnet_t* out);
+int aadff_psfnet_destroy(aadff_psfnet_t net);
+
+/* Replaces the slice loop of the training scripts (2_aber_aware_dff_aif.py:108-114,166-176):
+ * S calls of PSFNet.render (deeplens/psfnet.py:393-441, which calls MLP.forward
+ * deeplens/psfnet_arch.py:44-47 and local_psf_render deeplens/render_psf.py:76-107) and the
+ * torch.stack, as ONE launch.  S = 1 with strides {C*H*W, H*W, 0, W, 1} is PSFNet.render itself.
+ *   img    [N,C,H,W]  all-in-focus image, device
+ *   depth  [N,H,W]    depth in mm, <= 0 (0 = invalid), device
+ *   foc    [N,S]      focus distance per image and slice in mm, < 0, device
+ *   out               device; element strides for (n, c, s, h, w) in out_strides
+ *   d_min, d_max      PSFNet.d_min / d_max (-200, -20000)  (deeplens/psfnet.py:32-33)          */
+int aadff_render_stack_f32(aadff_psfnet_t net, const float* img, const float* depth, const float* foc, float* out,
+                           const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                           float d_max, int mode, void* stream);
+
+/* Same operation with HOST buffers (out is dense [N,C,S,H,W]): copies in, renders, copies
+ * out and synchronises, using a workspace and a stream owned by the handle.  This is the call
+ * the end-to-end benchmark times.                                                              */
+int aadff_render_stack_host_f32(aadff_psfnet_t net, const float* img, const float* depth, const float* foc,
+                                float* out, int N, int C, int S, int H, int W, float d_min, float d_max, int mode);
+
+/* Replaces PSFNet.pred (deeplens/psfnet.py:375-390) for arbitrary probes:
+ *   inp [M,4] (x, y, z, foc_z) -> psf [M, ks*ks], L1-normalised; fp32 arithmetic; device ptrs. */
+int aadff_psfnet_pred_f32(aadff_psfnet_t net, const float* inp, float* psf, int64_t M, void* stream);
+
+/* Replaces local_psf_render (deeplens/render_psf.py:76-107) for a PSF tensor in memory:
+ *   img [N,C,H,W], psf [N,H,W,ks,ks] -> out [N,C,H,W]; device pointers.                        */
+int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, int N, int C, int H, int W, int ks,
+                               void* stream);
+
+/* Number of kernels launched by this library in the calling process (bench bookkeeping).      */
+int64_t aadff_launch_count(void);
+
+/* Test hooks (used by tests/ only): a single-tile tcgen05 GEMM through the same operand
+ * packing, descriptors and TMEM read-back as the fused kernel (host pointers, synchronous),
+ * and the descriptor-convention probe it controls.                                            */
+int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N, int device);
+int aadff_debug_set_desc_swap(int swap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AADFF_H_ */

@@ -1,0 +1,166 @@
+"""GPU bring-up diagnostics (not a pytest file): each stage runs in its own subprocess under a
+hard timeout so that a hung kernel cannot take the whole box-call with it.
+
+    python tests/gpu_diag.py [stage ...]        # default: all stages, log to gpurun_out/diag.log
+"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def stage_umma():
+    import numpy as np
+    import ctypes
+    import aadff_b200
+    nat = aadff_b200.native
+    rng = np.random.default_rng(0)
+    for swap in (0, 1):
+        nat.lib.aadff_debug_set_desc_swap(swap)
+        for K, N in [(32, 16), (64, 256), (256, 256), (256, 128), (256, 208)]:
+            A = rng.standard_normal((128, K)).astype(np.float32)
+            B = rng.standard_normal((N, K)).astype(np.float32)
+            D = np.zeros((128, N), np.float32)
+            rc = nat.lib.aadff_debug_umma_gemm(A.ctypes.data, B.ctypes.data, D.ctypes.data, K, N, 0)
+            if rc:
+                print(f"swap={swap} K={K} N={N}: rc={rc} {nat.lib.aadff_last_error().decode()}")
+                continue
+            ref = A.astype(np.float16).astype(np.float32) @ B.astype(np.float16).astype(np.float32).T
+            err = np.abs(D - ref).max()
+            print(f"swap={swap} K={K} N={N}: max|D-ref|={err:.3e}  (|ref|max={np.abs(ref).max():.2f})", flush=True)
+    nat.lib.aadff_debug_set_desc_swap(0)
+
+
+def _lens(ks=11, mode="parity"):
+    import torch
+    import aadff_b200
+    lens = aadff_b200.PSFNet(kernel_size=ks, device="cuda", mode=mode)
+    if ks == 11:
+        lens.load_net(os.path.join(ROOT, "tests/golden/rf50mm_PSFNet480x640_ks11.pkl"))
+    return lens
+
+
+def _check(name, out, ref):
+    d = (out.cpu() - ref).abs()
+    print(f"{name}: max-abs {float(d.max()):.3e}  mean-abs {float(d.mean()):.3e}", flush=True)
+
+
+def stage_fp32():
+    import numpy as np
+    import torch
+    from conftest import analytic_rgbd, load_golden
+    lens = _lens(mode="fp32")
+    g = load_golden("kat_a_pred.npz")
+    _check("pred kat_a", lens.pred(torch.from_numpy(g["inp"]).cuda()), torch.from_numpy(g["psf"]))
+    for N, H, W in [(1, 48, 64), (2, 64, 64)]:
+        g = load_golden(f"kat_b_{N}x{H}x{W}.npz")
+        img, dm = analytic_rgbd(N, H, W)
+        out = lens.render(img.cuda(), -dm.cuda() * 1e3, torch.from_numpy(g["foc"]).cuda())
+        _check(f"fp32 render kat_b {N}x{H}x{W}", out, torch.from_numpy(g["out"]))
+    g = load_golden("kat_d_gather_0.npz")
+    import aadff_b200
+    out = aadff_b200.local_psf_render(torch.from_numpy(g["img"]).cuda(), torch.from_numpy(g["psf"]).cuda(), int(g["ks"]))
+    _check("gather kat_d_0", out, torch.from_numpy(g["out"]))
+
+
+def _tc(mode, swap=0):
+    import torch
+    import aadff_b200
+    from conftest import analytic_rgbd, load_golden
+    aadff_b200.native.lib.aadff_debug_set_desc_swap(swap)
+    lens = _lens(mode=mode)
+    for N, H, W in [(1, 48, 64), (2, 64, 64)]:
+        g = load_golden(f"kat_b_{N}x{H}x{W}.npz")
+        img, dm = analytic_rgbd(N, H, W)
+        out = lens.render(img.cuda(), -dm.cuda() * 1e3, torch.from_numpy(g["foc"]).cuda())
+        torch.cuda.synchronize()
+        _check(f"{mode} (swap={swap}) render kat_b {N}x{H}x{W}", out, torch.from_numpy(g["out"]))
+    g = load_golden("kat_e_stack_2x40x56.npz")
+    out = lens.render_stack(torch.from_numpy(g["img"]).cuda(), -torch.from_numpy(g["depth_m"]).cuda() * 1e3,
+                            -torch.from_numpy(g["foc_m"]).cuda() * 1e3)
+    _check(f"{mode} stack kat_e", out, torch.from_numpy(g["out"]))
+
+
+def stage_tc_parity():
+    _tc("parity")
+
+
+def stage_tc_parity_swap():
+    _tc("parity", swap=1)
+
+
+def stage_tc_fast():
+    _tc("fast")
+    _tc("mixed")
+
+
+def stage_tc_ks31():
+    import torch
+    from conftest import load_golden
+    from oracle import focal_stack_oracle as orc
+    g = load_golden("kat_g_ks31_1x40x48.npz")
+    Ws, bs = orc.seeded_psfnet_weights(31, seed=int(g["weight_seed"]))
+    gen = torch.Generator().manual_seed(int(g["bias_seed"]))
+    bs = [(torch.rand(b.shape, generator=gen) - 0.5) * 0.2 for b in bs]
+    for mode in ("fp32", "parity", "fast"):
+        lens = _lens(ks=31, mode=mode)
+        sd = {}
+        for l, (W, b) in enumerate(zip(Ws, bs)):
+            sd[f"net.{2 * l}.weight"], sd[f"net.{2 * l}.bias"] = W, b
+        lens.psfnet.load_state_dict(sd)
+        out = lens.render(torch.from_numpy(g["img"]).cuda(), -torch.from_numpy(g["depth_m"]).cuda() * 1e3,
+                          torch.from_numpy(g["foc"]).cuda())
+        torch.cuda.synchronize()
+        _check(f"{mode} ks31 kat_g", out, torch.from_numpy(g["out"]))
+
+
+def stage_speed():
+    import torch
+    from oracle import focal_stack_oracle as orc
+    for (N, S, H, W, ks, modes) in [(1, 5, 512, 512, 11, ("parity", "mixed", "fast", "fp32")),
+                                    (16, 5, 256, 256, 11, ("parity", "fast")),
+                                    (1, 2, 1080, 1920, 31, ("parity", "fast"))]:
+        img, dm = orc.synthetic_rgbd(N, H, W, seed=1234)
+        foc = -orc.synthetic_focus(dm, S).cuda() * 1e3
+        img, dep = img.cuda(), -dm.cuda() * 1e3
+        for mode in modes:
+            lens = _lens(ks=ks, mode=mode)
+            for _ in range(2):
+                out = lens.render_stack(img, dep, foc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 3 if mode == "fp32" else 10
+            e0.record()
+            for _ in range(iters):
+                out = lens.render_stack(img, dep, foc)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            print(f"speed N{N} S{S} {H}x{W} ks{ks} {mode}: {ms:.3f} ms  {N * S * H * W / ms / 1e3:.1f} Mpix*slices/s",
+                  flush=True)
+
+
+STAGES = {k[6:]: v for k, v in list(globals().items()) if k.startswith("stage_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--run":
+        STAGES[sys.argv[2]]()
+        sys.exit(0)
+    names = sys.argv[1:] or ["umma", "fp32", "tc_parity", "tc_parity_swap", "tc_fast", "tc_ks31", "speed"]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a")
+    for name in names:
+        t0 = time.time()
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--run", name], capture_output=True,
+                                 text=True, timeout=int(os.environ.get("DIAG_TIMEOUT", "150")))
+            txt = f"=== {name} (rc={res.returncode}, {time.time() - t0:.1f}s)\n{res.stdout}{res.stderr[-3000:]}\n"
+        except subprocess.TimeoutExpired as ex:
+            txt = f"=== {name} TIMEOUT after {time.time() - t0:.1f}s\n{ex.stdout or ''}\n{ex.stderr or ''}\n"
+        print(txt, flush=True)
+        log.write(txt)
+        log.flush()
