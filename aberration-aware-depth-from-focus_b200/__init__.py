@@ -22,5 +22,6 @@ from deeplens.psfnet import PSFNet, ThinLens, DMIN, DMAX         # noqa: E402
 from deeplens.render_psf import local_psf_render                 # noqa: E402
 from dff.factory import get_lens                                 # noqa: E402
 from dff.utils import select_focus_dist                          # noqa: E402
+import sharding                                                  # noqa: E402
 
-__all__ = ["native", "PSFNet", "ThinLens", "local_psf_render", "get_lens", "select_focus_dist", "DMIN", "DMAX"]
+__all__ = ["native", "sharding", "PSFNet", "ThinLens", "local_psf_render", "get_lens", "select_focus_dist", "DMIN", "DMAX"]

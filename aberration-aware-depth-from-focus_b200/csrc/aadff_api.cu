@@ -22,6 +22,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_desc_swap{0};
+std::atomic<unsigned long long*> g_trace{nullptr};
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -105,6 +106,12 @@ int aadff_debug_set_desc_swap(int swap) {
     g_desc_swap.store(swap ? 1 : 0);
     return AADFF_OK;
 }
+
+int aadff_debug_set_trace(void* device_buffer) {
+    g_trace.store(static_cast<unsigned long long*>(device_buffer));
+    return AADFF_OK;
+}
+int aadff_debug_trace_entries(void) { return TC_TRACE_N; }
 
 int aadff_psfnet_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
                         int ks, int device, aadff_psfnet_t* out) {
@@ -253,6 +260,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
     P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
     P.swap_lbo_sbo = (uint32_t)g_desc_swap.load();
+    P.trace = g_trace.load();
     // shared-memory carve-up
     const uint32_t halo_bytes = (uint32_t)ra.C * (TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 4;
     const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + 256;

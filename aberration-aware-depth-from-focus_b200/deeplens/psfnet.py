@@ -113,6 +113,8 @@ class PSFNet(nn.Module):
         nat = self.native()
         N, C, H, W = img.shape
         S = foc.shape[1]
+        if out.numel() == 0:            # empty batch: nothing to launch (data_ptr() of an empty tensor is NULL)
+            return
         arr = (_nat.ctypes.c_int64 * 5)(*strides)
         with torch.cuda.device(img.device):
             _nat.check(_nat.lib.aadff_render_stack_f32(

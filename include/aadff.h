@@ -85,6 +85,10 @@ int64_t aadff_launch_count(void);
  * and the descriptor-convention probe it controls.                                            */
 int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N, int device);
 int aadff_debug_set_desc_swap(int swap);
+/* Event trace of CTA 0 of the fused kernel: device buffer of 4 * aadff_debug_trace_entries()
+ * uint64 (zero-filled by the caller), NULL switches tracing off.  See tests/gpu_trace.py.    */
+int aadff_debug_set_trace(void* device_buffer);
+int aadff_debug_trace_entries(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,293 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called the way the reference's scripts call
+it (deeplens.psfnet.PSFNet / deeplens.render_psf.local_psf_render -> C ABI -> sm_100a kernels),
+against (1) golden vectors produced by the reference itself, (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (max-abs on [0,1] images, fp32):
+  parity mode (tcgen05, fp16 hi/lo split, 3 terms)   1e-4   -- north_star's bar; observed ~7e-6
+  fp32 mode   (CUDA cores)                           5e-6
+  mixed mode                                         1e-3
+  fast mode   (single fp16 term)                     3e-2 max, 3e-4 mean  (stated tolerance of that mode)
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, analytic_rgbd, load_golden
+from oracle import focal_stack_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"parity": 1e-4, "fp32": 5e-6, "mixed": 1e-3, "fast": 3e-2}
+CKPT = os.path.join(GOLDEN, "rf50mm_PSFNet480x640_ks11.pkl")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import aadff_b200
+    return aadff_b200
+
+
+@pytest.fixture(scope="module")
+def lens(pkg):
+    from deeplens.psfnet import PSFNet          # the reference's import line
+    l = PSFNet(filename='./lenses/rf50mm/lens.json', sensor_res=(480, 640), kernel_size=11)
+    l.load_net(CKPT)
+    l.analysis()
+    return l
+
+
+@pytest.fixture(scope="module")
+def lens31(pkg):
+    g = load_golden("kat_g_ks31_1x40x48.npz")
+    Ws, bs = orc.seeded_psfnet_weights(31, seed=int(g["weight_seed"]))
+    gen = torch.Generator().manual_seed(int(g["bias_seed"]))
+    bs = [(torch.rand(b.shape, generator=gen) - 0.5) * 0.2 for b in bs]
+    l = pkg.PSFNet(kernel_size=31, device="cuda")
+    sd = {}
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        sd[f"net.{2 * i}.weight"], sd[f"net.{2 * i}.bias"] = W, b
+    l.psfnet.load_state_dict(sd)
+    return l
+
+
+def maxabs(a, b):
+    return float((a.detach().cpu().float() - b.detach().cpu().float()).abs().max())
+
+
+# --------------------------------------------------------------------------- tensor-core plumbing
+@pytest.mark.parametrize("K,N", [(32, 16), (64, 256), (256, 256), (256, 128), (256, 208)])
+def test_umma_gemm_matches_fp16_product(pkg, K, N):
+    """tcgen05.mma through the fused kernel's operand packing/descriptors/TMEM read-back."""
+    rng = np.random.default_rng(K * 1000 + N)
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    D = np.zeros((128, N), np.float32)
+    pkg.native.check(pkg.native.lib.aadff_debug_umma_gemm(A.ctypes.data, B.ctypes.data, D.ctypes.data, K, N, 0))
+    ref = A.astype(np.float16).astype(np.float64) @ B.astype(np.float16).astype(np.float64).T
+    assert np.abs(D - ref).max() < 2e-4
+
+
+# --------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("i", [0, 1, 2, 3, 4, "3d"])
+def test_gather_golden(pkg, i):
+    from deeplens.render_psf import local_psf_render
+    g = load_golden(f"kat_d_gather_{i}.npz")
+    out = local_psf_render(T(g["img"]).cuda(), T(g["psf"]).cuda(), int(g["ks"]))
+    assert out.shape == g["out"].shape
+    assert maxabs(out, T(g["out"])) < 5e-5 * int(g["ks"])
+
+
+def test_pred_golden(lens):
+    g = load_golden("kat_a_pred.npz")
+    psf = lens.pred(T(g["inp"]).cuda())
+    assert psf.shape == (64, 11, 11)
+    assert maxabs(psf, T(g["psf"])) < 1e-6
+    assert abs(float(psf[1, 5, 5]) - 0.810939252) < 1e-6          # SURVEY.md 8c literal
+    grid = lens.pred(T(g["inp"]).cuda().reshape(8, 8, 4))           # [H,W,4] -> [H,W,ks,ks]
+    assert grid.shape == (8, 8, 11, 11) and maxabs(grid.reshape(64, 11, 11), psf) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32", "mixed", "fast"])
+@pytest.mark.parametrize("N,H,W", [(1, 48, 64), (2, 64, 64)])
+def test_render_kat_b(lens, mode, N, H, W):
+    g = load_golden(f"kat_b_{N}x{H}x{W}.npz")
+    img, dm = analytic_rgbd(N, H, W)
+    out = lens.render(img.cuda(), -dm.cuda() * 1e3, T(g["foc"]).cuda(), mode=mode)
+    assert out.shape == (N, 3, H, W) and out.dtype == torch.float32 and out.is_cuda
+    assert maxabs(out, T(g["out"])) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32"])
+def test_render_kat_b_full_frame(lens, mode):
+    """0_warm_up.py's shape (BASELINE config c1): 1 x 480 x 640, foc -2400 mm."""
+    g = load_golden("kat_b_1x480x640.npz")
+    img, dm = analytic_rgbd(1, 480, 640)
+    out = lens.render(img.cuda(), -dm.cuda() * 1e3, T(g["foc"]).cuda(), mode=mode).cpu()
+    assert (out[:, :, ::8, ::8] - T(g["out_sub"])).abs().max() < TOL[mode]
+    assert (out[:, :, [0, 1, 239, 240, 478, 479], :] - T(g["out_rows"])).abs().max() < TOL[mode]
+    assert abs(float(out.double().sum()) - float(g["sum"])) < 1.0
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32"])
+def test_render_kat_c_depth_clamps(lens, mode):
+    g = load_golden("kat_c_clamp.npz")
+    img, dm = analytic_rgbd(1, 32, 32)
+    dm[:, :, :8] = 0.0
+    dm[:, :, 8:16] = 30.0
+    out = lens.render(img.cuda(), -dm.cuda() * 1e3, T(g["foc"]).cuda(), mode=mode)
+    assert maxabs(out, T(g["out"])) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32", "fast"])
+def test_stack_golden_ragged(lens, mode):
+    """2 x 40 x 56 (not a multiple of the 8x16 tile), S=5, focus from select_focus_dist."""
+    from dff.utils import select_focus_dist
+    g = load_golden("kat_e_stack_2x40x56.npz")
+    img, dm = T(g["img"]).cuda(), T(g["depth_m"]).cuda()
+    foc_m = select_focus_dist(dm, 5)
+    assert torch.allclose(foc_m.cpu(), T(g["foc_m"]), rtol=3e-7, atol=0)
+    foc_m = T(g["foc_m"]).cuda()
+    out = lens.render_stack(img, -dm * 1e3, -foc_m * 1e3, mode=mode)
+    assert out.shape == (2, 3, 5, 40, 56)
+    d = (out.cpu() - T(g["out"])).abs()
+    assert float(d.max()) < TOL[mode]
+    if mode == "fast":
+        assert float(d.mean()) < 3e-4
+    # the reference's own loop: one render per slice, stacked on dim 2 -- bit-identical
+    loop = torch.stack([lens.render(img, -dm * 1e3, -foc_m[:, s] * 1e3, mode=mode) for s in range(5)], dim=2)
+    assert torch.equal(loop, out)
+    # DFVNet layout
+    assert torch.equal(lens.render_stack(img, -dm * 1e3, -foc_m * 1e3, layout="BSCHW", mode=mode),
+                       out.permute(0, 2, 1, 3, 4))
+
+
+def test_render_3d_branch(lens):
+    g = load_golden("kat_e_render3d.npz")
+    out = lens.render(T(g["img"]).cuda(), -T(g["depth_m"]).cuda() * 1e3, float(g["foc"]))
+    assert out.shape == (1, 3, 40, 56)
+    assert maxabs(out, T(g["out"])) < TOL["parity"]
+    with pytest.raises(ValueError):
+        lens.render(torch.rand(4, 4).cuda(), torch.rand(4, 4).cuda(), -1000.0)
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32", "fast"])
+def test_ks31_golden(lens31, mode):
+    g = load_golden("kat_g_ks31_1x40x48.npz")
+    out = lens31.render(T(g["img"]).cuda(), -T(g["depth_m"]).cuda() * 1e3, T(g["foc"]).cuda(), mode=mode)
+    assert maxabs(out, T(g["out"])) < TOL[mode]
+    probe = lens31.pred(torch.tensor([[0.1, -0.2, 0.3, 0.4]]).cuda())
+    assert maxabs(probe, T(g["psf_probe"])) < 1e-6
+
+
+def test_thinlens_and_focus_golden(pkg):
+    from deeplens.psfnet import ThinLens
+    from dff.utils import select_focus_dist
+    g = load_golden("kat_h_thinlens.npz")
+    tl = ThinLens(foc_len=float(g["foc_len"]), fnum=float(g["fnum"]), kernel_size=11,
+                  sensor_size=[float(v) for v in g["sensor_size"]], sensor_res=(40, 56)).to("cuda")
+    out = tl.render(T(g["img"]).cuda(), -T(g["depth_m"]).cuda() * 1e3, T(g["foc"]).cuda())
+    assert maxabs(out, T(g["out"])) < 5e-6
+    g = load_golden("kat_f_select_focus.npz")
+    # on the GPU torch divides by a Python scalar as multiply-by-reciprocal: 1 ulp from the CPU golden
+    assert torch.allclose(select_focus_dist(T(g["depth_m"]).cuda(), 5).cpu(), T(g["out"]), rtol=3e-7, atol=0)
+    assert torch.allclose(select_focus_dist(T(g["depth_m"]).cuda(), 8).cpu(), T(g["out8"]), rtol=3e-7, atol=0)
+
+
+# --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
+@pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17), (2, 3, 7, 130)])
+def test_edge_shapes_vs_oracle(lens, rf50mm_weights, N, C, H, W):
+    g = torch.Generator().manual_seed(N * 1000 + H * 10 + W)
+    img = torch.rand(N, C, H, W, generator=g)
+    dm = 0.3 + 6 * torch.rand(N, 1, H, W, generator=g)
+    foc = -(500 + 4000 * torch.rand(N, generator=g))
+    ref = orc.render(*rf50mm_weights, img, -dm * 1e3, foc, 11)
+    for mode in ("parity", "fp32"):
+        out = lens.render(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode=mode)
+        assert out.shape == (N, C, H, W)
+        assert maxabs(out, ref) < TOL[mode], mode
+
+
+def test_empty_batch_and_inputs_untouched(lens):
+    img = torch.rand(0, 3, 16, 16).cuda()
+    out = lens.render(img, torch.rand(0, 1, 16, 16).cuda(), torch.rand(0).cuda())
+    assert out.shape == (0, 3, 16, 16)
+    img = torch.rand(1, 3, 24, 24).cuda()
+    dep = -(torch.rand(1, 1, 24, 24).cuda() * 4000 + 300)
+    foc = torch.tensor([-1500.0]).cuda()
+    keep = (img.clone(), dep.clone(), foc.clone())
+    lens.render(img, dep, foc)
+    assert torch.equal(img, keep[0]) and torch.equal(dep, keep[1]) and torch.equal(foc, keep[2])
+
+
+def test_weight_update_rebuilds_device_copy(pkg):
+    l = pkg.PSFNet(kernel_size=11, device="cuda")
+    l.load_net(CKPT)
+    img, dm = analytic_rgbd(1, 32, 32)
+    a = l.render(img.cuda(), -dm.cuda() * 1e3, torch.tensor([-900.0]).cuda())
+    with torch.no_grad():
+        l.psfnet.net[20].bias.add_(torch.linspace(-3, 3, 121, device="cuda"))
+    b = l.render(img.cuda(), -dm.cuda() * 1e3, torch.tensor([-900.0]).cuda())
+    assert maxabs(a, b) > 1e-3
+    sd = torch.load(CKPT, map_location="cpu")
+    assert set(l.psfnet.state_dict().keys()) == set(sd.keys())
+
+
+def test_host_buffer_entry_point(pkg, lens):
+    nat = pkg.native
+    img, dm = orc.synthetic_rgbd(2, 40, 48, seed=3)
+    foc = -orc.synthetic_focus(dm, 4) * 1e3
+    dep = (-dm * 1e3).reshape(2, 40, 48).contiguous()
+    out = torch.empty(2, 3, 4, 40, 48)
+    nat.check(nat.lib.aadff_render_stack_host_f32(lens.native().handle, img.data_ptr(), dep.data_ptr(),
+                                                  foc.contiguous().data_ptr(), out.data_ptr(), 2, 3, 4, 40, 48,
+                                                  -200.0, -20000.0, nat.MODE_PARITY))
+    dev = lens.render_stack(img.cuda(), dep.cuda(), foc.cuda(), mode="parity")
+    assert torch.equal(out, dev.cpu())
+
+
+def test_c_abi_error_codes(pkg, lens):
+    nat = pkg.native
+    h = lens.native().handle
+    s = (ctypes.c_int64 * 5)(1, 1, 1, 1, 1)
+    assert nat.lib.aadff_render_stack_f32(h, None, None, None, None, s, 1, 3, 1, 8, 8, -200.0, -20000.0, 0, None) == -1
+    assert nat.lib.aadff_render_stack_f32(h, 8, 8, 8, 8, s, 1, 3, 1, 8, 8, -200.0, -20000.0, 7, None) == -1
+    assert nat.lib.aadff_local_psf_render_f32(8, 8, 8, 1, 3, 8, 8, 4, None) == -1          # even kernel size
+    assert b"kernel size" in nat.lib.aadff_last_error()
+    with pytest.raises(nat.AadffError):
+        nat.NativePSFNet([np.zeros((64, 4), np.float32), np.zeros((9, 64), np.float32)],
+                         [np.zeros(64, np.float32), np.zeros(9, np.float32)], 5, 0)      # 3*3 != 5*5
+
+
+# --------------------------------------------------------------------------- properties at BASELINE sizes
+def test_c2_constant_image_is_fixed_point(lens):
+    """sum(PSF) = 1  =>  a constant image renders to itself (c2: 5 x 512 x 512)."""
+    _, dm = orc.synthetic_rgbd(1, 512, 512, seed=1234)
+    foc = -orc.synthetic_focus(dm, 5) * 1e3
+    img = torch.full((1, 3, 512, 512), 0.625)
+    for mode in ("parity", "fast"):
+        out = lens.render_stack(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode=mode)
+        assert float((out - 0.625).abs().max()) < 2e-6, mode
+
+
+def test_c2_tensor_core_vs_fp32_full_size(lens):
+    img, dm = orc.synthetic_rgbd(1, 512, 512, seed=1234)
+    foc = -orc.synthetic_focus(dm, 5) * 1e3
+    ref = lens.render_stack(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode="fp32")
+    out = lens.render_stack(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode="parity")
+    assert float((out - ref).abs().max()) < TOL["parity"]
+    lo = torch.nn.functional.pad(img, (5, 5, 5, 5), mode="replicate").cuda()
+    mn = -torch.nn.functional.max_pool2d(-lo, 11, 1)
+    mx = torch.nn.functional.max_pool2d(lo, 11, 1)
+    assert bool(((out >= mn.unsqueeze(2) - 1e-5) & (out <= mx.unsqueeze(2) + 1e-5)).all())   # convex combination
+
+
+def test_c3_batch_independence(lens):
+    """c3 (16 x 5 x 256 x 256): rendering the batch == rendering each image alone, bit for bit."""
+    img, dm = orc.synthetic_rgbd(16, 256, 256, seed=77)
+    foc = -orc.synthetic_focus(dm, 5) * 1e3
+    img, dep, foc = img.cuda(), -dm.cuda() * 1e3, foc.cuda()
+    full = lens.render_stack(img, dep, foc)
+    for n in (0, 7, 15):
+        assert torch.equal(full[n:n + 1], lens.render_stack(img[n:n + 1], dep[n:n + 1], foc[n:n + 1]))
+    ref = lens.render_stack(img[3:5], dep[3:5], foc[3:5], mode="fp32")
+    assert float((full[3:5] - ref).abs().max()) < TOL["parity"]
+
+
+def test_c4_large_kernel_full_frame(lens31):
+    """c4's frame (1080 x 1920, k = 31), two slices: tensor-core path vs fp32 path + fixed point."""
+    img, dm = orc.synthetic_rgbd(1, 1080, 1920, seed=9)
+    foc = -orc.synthetic_focus(dm, 2) * 1e3
+    img, dep, foc = img.cuda(), -dm.cuda() * 1e3, foc.cuda()
+    out = lens31.render_stack(img, dep, foc, mode="parity")
+    ref = lens31.render_stack(img, dep, foc[:, :1], mode="fp32")
+    assert float((out[:, :, :1] - ref).abs().max()) < TOL["parity"]
+    const = lens31.render_stack(torch.full_like(img, 0.25), dep, foc[:, 1:], mode="parity")
+    assert float((const - 0.25).abs().max()) < 2e-6

@@ -1,0 +1,177 @@
+"""CPU-side tests (pytest -m "not gpu"): the C-ABI library loads and exports every symbol the
+header declares, argument validation works without a device, the Python drop-in surface mirrors
+the reference's, nothing falls back to a CPU path, and the multi-rank partitioning logic gathers
+to the single-rank result under a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+CKPT = os.path.join(GOLDEN, "rf50mm_PSFNet480x640_ks11.pkl")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import aadff_b200
+    return aadff_b200
+
+
+def test_library_exports_every_header_symbol(pkg):
+    nat = pkg.native
+    with open(os.path.join(ROOT, "include", "aadff.h")) as f:
+        declared = sorted(set(re.findall(r"\b(aadff_[a-z0-9_]+)\s*\(", f.read())))
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(nat.lib, name), name
+    assert nat.lib.aadff_version() == 100
+    assert nat.lib.aadff_launch_count() >= 0
+    sass_free = subprocess.run(["nm", "-D", nat.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", sass_free), f"{name} not an exported text symbol"
+
+
+def test_argument_validation_needs_no_device(pkg):
+    lib = pkg.native.lib
+    assert lib.aadff_local_psf_render_f32(None, None, None, 1, 3, 8, 8, 11, None) == -1
+    assert b"null" in lib.aadff_last_error()
+    assert lib.aadff_local_psf_render_f32(8, 8, 8, 1, 3, 8, 8, 10, None) == -1
+    assert lib.aadff_psfnet_pred_f32(None, None, None, 4, None) == -1
+    assert lib.aadff_psfnet_create(None, None, None, 11, 11, 0, None) == -1
+    assert lib.aadff_psfnet_destroy(None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks behaviour on a box without a GPU")
+def test_no_cpu_fallback(pkg):
+    """Without a device every compute entry fails loudly; nothing silently computes on the host."""
+    from deeplens.psfnet import PSFNet
+    from deeplens.render_psf import local_psf_render
+    lens = PSFNet(kernel_size=11, device="cpu")
+    lens.load_net(CKPT)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lens.render(torch.rand(1, 3, 8, 8), -torch.rand(1, 1, 8, 8) * 1000, torch.tensor([-1000.0]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lens.pred(torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        local_psf_render(torch.rand(1, 3, 8, 8), torch.rand(1, 8, 8, 3, 3), 3)
+    with pytest.raises(pkg.native.AadffError):
+        pkg.native.NativePSFNet([np.zeros((64, 4), np.float32), np.zeros((256, 64), np.float32),
+                                 np.zeros((9, 256), np.float32)], [np.zeros(64, np.float32), np.zeros(256, np.float32),
+                                                                   np.zeros(9, np.float32)], 3, 0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "aberration-aware-depth-from-focus_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    text = fh.read()
+                assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_python_surface_mirrors_reference(pkg):
+    from deeplens.psfnet import PSFNet, ThinLens, DMIN, DMAX
+    from deeplens.psfnet_arch import MLP
+    from dff.factory import get_lens
+    lens = PSFNet(filename="./lenses/rf50mm/lens.json", model_name="mlp", kernel_size=11, sensor_res=(480, 640),
+                  device="cpu")
+    assert (lens.d_min, lens.d_max, lens.kernel_size, lens.device) == (-DMIN, -DMAX, 11, "cpu")
+    assert isinstance(lens.psfnet, MLP) and sum(p.numel() for p in lens.psfnet.parameters()) == 574393
+    sd = torch.load(CKPT, map_location="cpu")
+    assert list(lens.psfnet.state_dict().keys()) == list(sd.keys())
+    lens.load_net(CKPT)
+    assert torch.equal(lens.psfnet.state_dict()["net.20.bias"], sd["net.20.bias"])
+    d = torch.tensor([0.0, -200.0, -10100.0, -20000.0, -30000.0])
+    assert torch.allclose(lens.depth2z(d), torch.tensor([0.0, 0.0, 0.5, 1.0, 1.0]))
+    assert torch.allclose(lens.z2depth(lens.depth2z(d[1:4])), d[1:4])
+    lens.analysis()
+    with pytest.raises(NotImplementedError):
+        PSFNet(model_name="siren", device="cpu")
+    args = {"ks": 11, "res": (480, 640), "device": "cpu",
+            "train": {"lens": "./lenses/rf50mm/lens.json", "psfnet_path": CKPT},
+            "test": {"lens": "thinlens", "foc_len": 50.0, "fnum": 1.8, "sensor_size": ["36", "24"]}}
+    train_lens, test_lens = get_lens(args)
+    assert isinstance(train_lens, PSFNet) and isinstance(test_lens, ThinLens)
+    assert abs(test_lens.ps - 36.0 / 480) < 1e-12
+    coc = test_lens.coc(torch.tensor([-1000.0, -2000.0]), torch.tensor([-2000.0, -2000.0]))
+    assert coc[1] == pytest.approx(0.1) and coc[0] > 1.0
+
+
+def test_select_focus_dist_matches_reference_golden():
+    from dff.utils import select_focus_dist
+    g = load_golden("kat_f_select_focus.npz")
+    d = torch.from_numpy(g["depth_m"])
+    assert torch.equal(select_focus_dist(d, 5), torch.from_numpy(g["out"]))
+    assert torch.equal(select_focus_dist(d, 8), torch.from_numpy(g["out8"]))
+    with pytest.raises(AssertionError):
+        select_focus_dist(d, 3)
+
+
+def test_item_partition_is_exact_and_balanced(pkg):
+    sh = pkg.sharding
+    for N, S in [(16, 5), (1, 10), (3, 7), (1, 1)]:
+        for world in (1, 2, 4, 8):
+            seen = []
+            sizes = []
+            for r in range(world):
+                runs = sh.local_runs(N, S, world, r)
+                items = [(n, s) for (n, s0, s1) in runs for s in range(s0, s1)]
+                sizes.append(len(items))
+                seen += items
+            assert seen == [(n, s) for n in range(N) for s in range(S)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import aadff_b200
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT={port!r}, RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+
+class FakeLens:          # stands in for PSFNet.render_stack: deterministic, per-item, CPU
+    def render_stack(self, img, depth, foc):
+        return img[:, :, None] * foc[:, None, :, None, None] + depth[:, :, None]
+
+g = torch.Generator().manual_seed(0)
+img, depth, foc = torch.rand(3, 2, 4, 5, generator=g), torch.rand(3, 1, 4, 5, generator=g), torch.rand(3, 7, generator=g)
+full, runs = aadff_b200.sharding.render_stack_sharded(FakeLens(), img, depth, foc, rank, world)
+ref = FakeLens().render_stack(img, depth, foc)
+assert full.shape == ref.shape and torch.equal(full, ref), "gathered stack differs"
+local, _ = aadff_b200.sharding.render_stack_sharded(FakeLens(), img, depth, foc, rank, world, gather=False)
+assert local.shape[0] == sum(s1 - s0 for _, s0, s1 in runs)
+dist.destroy_process_group()
+print("rank", rank, "ok", runs)
+"""
+
+
+def test_sharded_render_gathers_to_single_rank_result_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=str(29500 + os.getpid() % 2000)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU arm) must emit one JSON line with the contract keys."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "cpu_baseline", "e2e", "config"):
+        assert key in line
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
