@@ -221,7 +221,9 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         if (rc) { aadff_psfnet_destroy(h); return rc; }
         rc = upload(w0b0, &h->d_w0b0);
         if (rc) { aadff_psfnet_destroy(h); return rc; }
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      h->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       h->smem_optin));
     }
     *out = h;
@@ -276,7 +278,10 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.off_bar = P.off_red + TC_M * 5 * 4;
     const uint32_t smem = P.off_bar + 256;
     const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
-    fused_psfnet_render_kernel<<<grid, TC_NT, smem, st>>>(P);
+    if (P.trace != nullptr)
+        fused_psfnet_render_kernel<true><<<grid, TC_NT, smem, st>>>(P);
+    else
+        fused_psfnet_render_kernel<false><<<grid, TC_NT, smem, st>>>(P);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;

@@ -81,16 +81,20 @@ struct TcParams {
 
 // Event trace (debug): role 0 producer, 1 MMA issuer, 2 epilogue warp e=0, 3 epilogue warp e=7.
 // Entry = (event code << 40) | (clock64 & 0xFFFFFFFFFF); only CTA 0 records, first TC_TRACE_N events.
+template <bool ON>
 struct TcTrace {
     unsigned long long* p;
     int n;
     __device__ __forceinline__ void init(unsigned long long* base, int role) {
-        p = (base != nullptr && blockIdx.x == 0) ? base + role * TC_TRACE_N : nullptr;
-        n = 0;
+        if (ON) {
+            p = (base != nullptr && blockIdx.x == 0) ? base + role * TC_TRACE_N : nullptr;
+            n = 0;
+        }
     }
     __device__ __forceinline__ void ev(unsigned code) {
-        if (p != nullptr && n < TC_TRACE_N) {
-            p[n++] = ((unsigned long long)code << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+        if (ON) {
+            if (p != nullptr && n < TC_TRACE_N)
+                p[n++] = ((unsigned long long)code << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
         }
     }
 };
@@ -128,6 +132,7 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_
 constexpr int TC_WARP_PRODUCER = TC_EPI_WARPS;       // warp 8
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;        // warp 9
 
+template <bool TRACE>
 __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -163,102 +168,108 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == TC_WARP_PRODUCER) {
-        // =========================================================== weight producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            TcTrace tr; tr.init(P.trace, 0);
-            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                for (int gi = 0; gi < P.n_groups; ++gi) {
-                    const TcGroup g = P.g[gi];
-                    const uint32_t bytes = (uint32_t)g.N * (TC_SLAB_K * 2);
-                    const int nparts = (g.terms == 3) ? 2 : 1;
-                    const uint8_t* src = P.wpack + g.w_off;
-                    for (int kc = 0; kc < g.K / TC_SLAB_K; ++kc) {
-                        for (int part = 0; part < nparts; ++part) {
-                            mbar_wait(bar_empty(stage), phase ^ 1);
-                            tr.ev(0x100 + gi);                       // slab load issued
+        // =========================================================== weight producer (converged warp)
+        int stage = 0;
+        uint32_t phase = 0;
+        TcTrace<TRACE> tr; tr.init(lane == 0 ? P.trace : nullptr, 0);
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            for (int gi = 0; gi < P.n_groups; ++gi) {
+                const uint32_t bytes = (uint32_t)P.g[gi].N * (TC_SLAB_K * 2);
+                const int nparts = (P.g[gi].terms == 3) ? 2 : 1;
+                const uint8_t* src = P.wpack + P.g[gi].w_off;
+                const int nkc = P.g[gi].K / TC_SLAB_K;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    for (int part = 0; part < nparts; ++part) {
+                        mbar_wait(bar_empty(stage), phase ^ 1);
+                        tr.ev(0x100 + gi);                       // slab load issued
+                        if (elect_one_sync()) {
                             mbar_arrive_expect_tx(bar_full(stage), bytes);
                             bulk_g2s(stage0 + stage * TC_STAGE_BYTES, src + (size_t)(kc * 2 + part) * bytes, bytes,
                                      bar_full(stage));
-                            if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == TC_WARP_MMA) {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t fphase = 0, aphase = 0, frphase = 0;     // bit j / bit b = parity to wait for next
-            unsigned long long gcount = 0;
-            TcTrace tr; tr.init(P.trace, 1);
-            // descriptors: everything but the 14-bit start-address field is loop invariant
-            const uint64_t da_hi = umma_smem_desc(a_hi, TC_A_LBO, 128);
-            const uint64_t da_lo = umma_smem_desc(a_lo, TC_A_LBO, 128);
-            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                for (int gi = 0; gi < P.n_groups; ++gi) {
-                    const TcGroup g = P.g[gi];
-                    const int buf = (int)(gcount & 1);
-                    if (gcount >= 2) {           // the epilogue must have drained group gcount-2
-                        mbar_wait(bar_accfree(buf), (frphase >> buf) & 1);
-                        frphase ^= 1u << buf;
+        // =========================================================== MMA issuer (converged warp, elected lane)
+        int stage = 0;
+        uint32_t fphase = 0, aphase = 0, frphase = 0;     // bit j / bit b = parity to wait for next
+        uint32_t gcount = 0;
+        TcTrace<TRACE> tr; tr.init(lane == 0 ? P.trace : nullptr, 1);
+        // descriptors: everything but the 14-bit start-address field (16-byte units) is loop invariant
+        const uint64_t da_hi = umma_smem_desc(a_hi, TC_A_LBO, 128);
+        const uint64_t da_lo = umma_smem_desc(a_lo, TC_A_LBO, 128);
+        constexpr uint32_t KSTEP_A = (2 * TC_A_LBO) >> 4;            // one K=16 step of A
+        constexpr uint32_t STAGE_STEP = TC_STAGE_BYTES >> 4;
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            for (int gi = 0; gi < P.n_groups; ++gi) {
+                const uint32_t gN = P.g[gi].N;
+                const int nkc = P.g[gi].K / TC_SLAB_K;
+                const bool three = P.g[gi].terms == 3;
+                const bool new_a = P.g[gi].new_a != 0;
+                const uint32_t buf = gcount & 1;
+                if (gcount >= 2) {           // the epilogue must have drained group gcount-2
+                    mbar_wait(bar_accfree(buf), (frphase >> buf) & 1);
+                    frphase ^= 1u << buf;
+                }
+                tc_fence_after_sync();
+                tr.ev(0x200 + gi);                               // group start (accumulator free)
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                const uint32_t idesc = umma_idesc_f16_f32(TC_M, gN);
+                const uint32_t kstep_b = (2 * gN * 16) >> 4;     // one K=16 step of B: 2 * LBO_B
+                const uint64_t db0 = umma_smem_desc(stage0, gN * 16, 128);
+                uint32_t acc = 0;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    if (new_a && (kc & 1) == 0) {
+                        const int j = kc >> 1;
+                        tr.ev(0x300 + j);                        // start waiting for A chunk j
+                        mbar_wait(bar_aready(j), (aphase >> j) & 1);
+                        aphase ^= 1u << j;
+                        tr.ev(0x400 + j);                        // A chunk j ready
                     }
+                    const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
+                    const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
+                    // ---- hi weight slab: Ah*Wh (+ Al*Wh)
+                    tr.ev(0x500 + kc);                           // start waiting for hi slab kc
+                    mbar_wait(bar_full(stage), fphase);
                     tc_fence_after_sync();
-                    tr.ev(0x200 + gi);                               // group start (accumulator free)
-                    const uint32_t d_tmem = tmem_base + buf * 256;
-                    const uint32_t idesc = umma_idesc_f16_f32(TC_M, g.N);
-                    const uint32_t lbo_b = (uint32_t)g.N * 16;
-                    const uint64_t db0 = umma_smem_desc(stage0, lbo_b, 128);
-                    const bool three = g.terms == 3;
-                    uint32_t acc = 0;
-                    for (int kc = 0; kc < g.K / TC_SLAB_K; ++kc) {
-                        if (g.new_a && (kc & 1) == 0) {
-                            const int j = kc >> 1;
-                            tr.ev(0x300 + j);                        // start waiting for A chunk j
-                            mbar_wait(bar_aready(j), (aphase >> j) & 1);
-                            aphase ^= 1u << j;
-                            tc_fence_after_sync();
-                            tr.ev(0x400 + j);                        // A chunk j ready
-                        }
-                        // descriptor deltas are in 16-byte units (address field)
-                        const uint64_t ka = (uint64_t)((uint32_t)(kc * 2) * (2 * TC_A_LBO) >> 4);
-                        const uint64_t kstep_a = (2 * TC_A_LBO) >> 4, kstep_b = (2 * lbo_b) >> 4;
-                        // ---- hi weight slab: Ah*Wh (+ Al*Wh)
-                        tr.ev(0x500 + kc);                           // start waiting for hi slab kc
-                        mbar_wait(bar_full(stage), fphase);
-                        tc_fence_after_sync();
-                        tr.ev(0x600 + kc);                           // hi slab landed
-                        uint64_t db = db0 + (uint64_t)((uint32_t)(stage * TC_STAGE_BYTES) >> 4);
-                        umma_f16_ss(d_tmem, da_hi + ka, db, idesc, acc);
-                        umma_f16_ss(d_tmem, da_hi + ka + kstep_a, db + kstep_b, idesc, 1);
-                        acc = 1;
+                    tr.ev(0x600 + kc);                           // hi slab landed
+                    if (elect_one_sync()) {
+                        const uint64_t db = db0 + (uint32_t)stage * STAGE_STEP;
+                        umma_f16_ss(d_tmem, ah, db, idesc, acc);
+                        umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
                         if (three) {
-                            umma_f16_ss(d_tmem, da_lo + ka, db, idesc, 1);
-                            umma_f16_ss(d_tmem, da_lo + ka + kstep_a, db + kstep_b, idesc, 1);
+                            umma_f16_ss(d_tmem, al, db, idesc, 1);
+                            umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
                         }
                         umma_commit(bar_empty(stage));
-                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
-                        if (three) {
-                            // ---- lo weight slab: Ah*Wl
-                            mbar_wait(bar_full(stage), fphase);
-                            tc_fence_after_sync();
-                            db = db0 + (uint64_t)((uint32_t)(stage * TC_STAGE_BYTES) >> 4);
-                            umma_f16_ss(d_tmem, da_hi + ka, db, idesc, 1);
-                            umma_f16_ss(d_tmem, da_hi + ka + kstep_a, db + kstep_b, idesc, 1);
-                            umma_commit(bar_empty(stage));
-                            if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
-                        }
                     }
-                    umma_commit(bar_accfull(buf));
-                    tr.ev(0x700 + gi);                               // group fully issued
-                    ++gcount;
+                    __syncwarp();
+                    acc = 1;
+                    if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                    if (three) {
+                        // ---- lo weight slab: Ah*Wl
+                        mbar_wait(bar_full(stage), fphase);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t db = db0 + (uint32_t)stage * STAGE_STEP;
+                            umma_f16_ss(d_tmem, ah, db, idesc, 1);
+                            umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
+                            umma_commit(bar_empty(stage));
+                        }
+                        __syncwarp();
+                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                    }
                 }
+                if (elect_one_sync()) umma_commit(bar_accfull(buf));
+                __syncwarp();
+                tr.ev(0x700 + gi);                               // group fully issued
+                ++gcount;
             }
         }
-        __syncwarp();
     } else {
         // =========================================================== epilogue / compute warps 0..7
         const int e = warp;                     // 0..7
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         const uint32_t a_row = (uint32_t)row * 16;
         uint32_t afphase = 0;
         unsigned long long gcount = 0;
-        TcTrace tr; tr.init((lane == 0 && (e == 0 || e == 7)) ? P.trace : nullptr, e == 0 ? 2 : 3);
+        TcTrace<TRACE> tr; tr.init((lane == 0 && (e == 0 || e == 7)) ? P.trace : nullptr, e == 0 ? 2 : 3);
         const float NEG_LOG2E = -1.4426950408889634f;
 
         // tile -> (image n, slice s, tile origin); depth / focus of this thread's pixel are fetched

@@ -133,6 +133,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // ----------------------------------------------------------------------------- misc
+// One lane of a fully converged warp.  Keeping the issuing warp converged (instead of branching on
+// lane == 0) lets ptxas keep descriptors in uniform registers and emit UTCHMMA/UTCBAR directly.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
