@@ -22,6 +22,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_desc_swap{0};
+std::atomic<int> g_dbg_flags{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
 
 int fail(int code, const std::string& msg) {
@@ -112,6 +113,10 @@ int aadff_debug_set_trace(void* device_buffer) {
     return AADFF_OK;
 }
 int aadff_debug_trace_entries(void) { return TC_TRACE_N; }
+int aadff_debug_set_flags(int flags) {
+    g_dbg_flags.store(flags);
+    return AADFF_OK;
+}
 
 int aadff_psfnet_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
                         int ks, int device, aadff_psfnet_t* out) {
@@ -263,20 +268,26 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
     P.swap_lbo_sbo = (uint32_t)g_desc_swap.load();
     P.trace = g_trace.load();
+    P.dbg = (uint32_t)g_dbg_flags.load();
     // shared-memory carve-up
     const uint32_t halo_bytes = (uint32_t)ra.C * (TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 4;
-    const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + 256;
-    int stages = TC_MAX_STAGES;
+    const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES;
+    int stages = 4;
     while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;
     if (stages < 2) return fail(AADFF_E_UNSUPPORTED, "shared memory budget exceeded for this kernel size / channel count");
-    P.n_stages = stages;
+    bool any_lo = false;
+    for (int i = 0; i < h->n_groups; ++i) any_lo |= (P.g[i].terms == 3);
     P.off_stage = 2 * TC_A_PART_BYTES;
     P.off_bias = P.off_stage + stages * TC_STAGE_BYTES;
     P.off_w0 = P.off_bias + (uint32_t)h->n_bias * 4;
     P.off_halo = P.off_w0 + 320 * 4;
     P.off_red = P.off_halo + halo_bytes;
     P.off_bar = P.off_red + TC_M * 5 * 4;
-    const uint32_t smem = P.off_bar + 256;
+    const uint32_t smem = P.off_bar + TC_BAR_BYTES;
+    // no layer needs lo operands (fast mode): the A_lo region doubles the ring to 128 KB, organised as four
+    // 32 KB stages (two packed K=32 slabs each) so that every issue iteration queues four MMAs
+    P.kslab = (!any_lo && stages == 4) ? 2 : 1;
+    P.n_stages = (P.kslab == 2) ? 4 : stages;
     const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
     if (P.trace != nullptr)
         fused_psfnet_render_kernel<true><<<grid, TC_NT, smem, st>>>(P);
@@ -423,6 +434,28 @@ int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(D, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return AADFF_OK;
+}
+
+
+int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps, int N, int epi_load,
+                           uint64_t* out_cycles, int device) {
+    if (!mmas_per_commit || !out_cycles || n_patterns < 1 || n_patterns > 31) return fail(AADFF_E_INVALID, "bad args");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    int* d_m = nullptr;
+    unsigned long long* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_m), n_patterns * sizeof(int)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_out), 64 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(d_m, mmas_per_commit, n_patterns * sizeof(int), cudaMemcpyHostToDevice));
+    const int smem = TC_A_PART_BYTES + 65536 + 64;
+    CUDA_TRY(cudaFuncSetAttribute(debug_mma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    debug_mma_timing_kernel<<<1, 128, smem>>>(d_out, n_patterns, d_m, reps, N, epi_load);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out_cycles, d_out, n_patterns * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_m);
+    cudaFree(d_out);
     return AADFF_OK;
 }
 

@@ -48,9 +48,10 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_NT = 64 + TC_EPI_THREADS;            // 320 threads
 constexpr int TC_MAX_GROUPS = 16;
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;        // 4 in the stage area (+ 4 in the A_lo region when no layer needs lo parts)
 constexpr int TC_MAX_KS = 31;
 constexpr int TC_MAX_C = 4;
+constexpr int TC_BAR_BYTES = 256;        // mbarriers (2*8 + 4 + 2 + 2) * 8 B + TMEM slot
 constexpr int TC_TRACE_N = 4096;         // trace entries per role
 
 struct TcGroup {            // one accumulation group: one layer, or one <=256-column block of the head
@@ -71,11 +72,13 @@ struct TcParams {
     TcGroup g[TC_MAX_GROUPS];
     int n_groups, n_hidden; // n_hidden = 9 (L1..L9); the rest are head blocks
     int n_bias, n_stages, kk;
+    int kslab;              // packed K=32 slabs per ring stage: 1 (any 3-term layer) or 2 (fast mode, 32 KB stages)
     int tiles_x, tiles_y;
     long long n_tiles;
     // shared-memory byte offsets
     uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar;
     uint32_t swap_lbo_sbo;  // debug: descriptor field convention probe
+    uint32_t dbg;           // what-if timing switches (results invalid): 1 = no weight copies, 2 = no A stores
     unsigned long long* trace;  // optional [4 roles][TC_TRACE_N] event log of CTA 0 (nullptr = off)
 };
 
@@ -141,6 +144,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
 
     const uint32_t a_hi = sbase, a_lo = sbase + TC_A_PART_BYTES;
     const uint32_t stage0 = sbase + P.off_stage;
+    // ring stage s: first four in the stage area, the rest (fast mode only) in the unused A_lo region
+    const int stage_bytes = P.kslab * TC_STAGE_BYTES, stages_in_area = 4 / P.kslab;
+    auto stage_addr = [&](int st) {
+        return st < stages_in_area ? stage0 + st * stage_bytes : a_lo + (st - stages_in_area) * stage_bytes;
+    };
     float* s_bias = reinterpret_cast<float*>(smem + P.off_bias);
     float* s_w0 = reinterpret_cast<float*>(smem + P.off_w0);
     float* s_halo = reinterpret_cast<float*>(smem + P.off_halo);
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 4 + b); };
     auto bar_accfree = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 6 + b); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 8));
+    static_assert(8 * (2 * TC_MAX_STAGES + 8) + 4 <= TC_BAR_BYTES, "barrier area too small");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
@@ -177,15 +186,21 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint32_t bytes = (uint32_t)P.g[gi].N * (TC_SLAB_K * 2);
                 const int nparts = (P.g[gi].terms == 3) ? 2 : 1;
                 const uint8_t* src = P.wpack + P.g[gi].w_off;
-                const int nkc = P.g[gi].K / TC_SLAB_K;
-                for (int kc = 0; kc < nkc; ++kc) {
+                const int kslab = P.kslab;
+                const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
+                for (int it = 0; it < nit; ++it) {
                     for (int part = 0; part < nparts; ++part) {
                         mbar_wait(bar_empty(stage), phase ^ 1);
-                        tr.ev(0x100 + gi);                       // slab load issued
+                        tr.ev(0x100 + gi);                       // stage load issued
                         if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(bar_full(stage), bytes);
-                            bulk_g2s(stage0 + stage * TC_STAGE_BYTES, src + (size_t)(kc * 2 + part) * bytes, bytes,
-                                     bar_full(stage));
+                            if (P.dbg & 1) {
+                                mbar_arrive(bar_full(stage));
+                            } else {
+                                mbar_arrive_expect_tx(bar_full(stage), bytes * kslab);
+                                for (int hs = 0; hs < kslab; ++hs)
+                                    bulk_g2s(stage_addr(stage) + hs * TC_STAGE_BYTES,
+                                             src + (size_t)((it * kslab + hs) * 2 + part) * bytes, bytes, bar_full(stage));
+                            }
                         }
                         __syncwarp();
                         if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
@@ -222,7 +237,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint32_t kstep_b = (2 * gN * 16) >> 4;     // one K=16 step of B: 2 * LBO_B
                 const uint64_t db0 = umma_smem_desc(stage0, gN * 16, 128);
                 uint32_t acc = 0;
-                for (int kc = 0; kc < nkc; ++kc) {
+                int prev_stage = -1;     // a stage is released (commit) only after the NEXT stage's MMAs are queued
+                const int kslab = P.kslab;
+                const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
+                for (int it = 0; it < nit; ++it) {
+                    const int kc = it * kslab;                   // first K=32 slab of this stage
                     if (new_a && (kc & 1) == 0) {
                         const int j = kc >> 1;
                         tr.ev(0x300 + j);                        // start waiting for A chunk j
@@ -232,39 +251,48 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     }
                     const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
-                    // ---- hi weight slab: Ah*Wh (+ Al*Wh)
-                    tr.ev(0x500 + kc);                           // start waiting for hi slab kc
+                    // ---- hi weight slab(s): Ah*Wh (+ Al*Wh)
+                    tr.ev(0x500 + kc);                           // start waiting for the hi stage
                     mbar_wait(bar_full(stage), fphase);
                     tc_fence_after_sync();
-                    tr.ev(0x600 + kc);                           // hi slab landed
+                    tr.ev(0x600 + kc);                           // hi stage landed
                     if (elect_one_sync()) {
-                        const uint64_t db = db0 + (uint32_t)stage * STAGE_STEP;
+                        const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
                         umma_f16_ss(d_tmem, ah, db, idesc, acc);
                         umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
+                        if (kslab == 2) {
+                            umma_f16_ss(d_tmem, ah + 2 * KSTEP_A, db + STAGE_STEP, idesc, 1);
+                            umma_f16_ss(d_tmem, ah + 3 * KSTEP_A, db + STAGE_STEP + kstep_b, idesc, 1);
+                        }
                         if (three) {
                             umma_f16_ss(d_tmem, al, db, idesc, 1);
                             umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
                         }
-                        umma_commit(bar_empty(stage));
+                        if (prev_stage >= 0) umma_commit(bar_empty(prev_stage));
                     }
                     __syncwarp();
                     acc = 1;
+                    prev_stage = stage;
                     if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
                     if (three) {
                         // ---- lo weight slab: Ah*Wl
                         mbar_wait(bar_full(stage), fphase);
                         tc_fence_after_sync();
                         if (elect_one_sync()) {
-                            const uint64_t db = db0 + (uint32_t)stage * STAGE_STEP;
+                            const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
                             umma_f16_ss(d_tmem, ah, db, idesc, 1);
                             umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
-                            umma_commit(bar_empty(stage));
+                            umma_commit(bar_empty(prev_stage));
                         }
                         __syncwarp();
+                        prev_stage = stage;
                         if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
                     }
                 }
-                if (elect_one_sync()) umma_commit(bar_accfull(buf));
+                if (elect_one_sync()) {
+                    umma_commit(bar_accfull(buf));               // the epilogue is waiting on this one
+                    umma_commit(bar_empty(prev_stage));
+                }
                 __syncwarp();
                 tr.ev(0x700 + gi);                               // group fully issued
                 ++gcount;
@@ -402,7 +430,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         v[6] = fmaxf(__uint_as_float(cur[i * 8 + 6]) + b1.z, 0.f);
                         v[7] = fmaxf(__uint_as_float(cur[i * 8 + 7]) + b1.w, 0.f);
                         const uint32_t off = (uint32_t)(j * 8 + hh * 4 + i) * TC_A_LBO + a_row;
-                        store_split8(v, a_hi + off, a_lo + off, need_lo);
+                        if (!(P.dbg & 2) || v[0] == 123.456f) store_split8(v, a_hi + off, a_lo + off, need_lo);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -538,6 +566,70 @@ debug_umma_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ 
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Debug microbenchmark: cost of issuing tcgen05.mma / tcgen05.commit from one converged warp.
+// Pattern p: `reps` x [ mmas_per_commit[p] MMAs (M128 x N x K16, smem operands) ; commit ].
+// out[p*2+0] = cycles until the issuing thread is done, out[p*2+1] = cycles until all MMAs retired.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas_per_commit, int reps, int N,
+                        int epi_load) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_sm = sbase, b_sm = sbase + TC_A_PART_BYTES;
+    const uint32_t bar_done = sbase + TC_A_PART_BYTES + 65536, bar_slab = bar_done + 8;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + TC_A_PART_BYTES + 65536 + 32);
+    for (int i = threadIdx.x; i < (TC_A_PART_BYTES + 65536) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(bar_done, 1); mbar_init(bar_slab, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(slot)));
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *slot;
+    uint32_t done_phase = 0;
+    for (int p = 0; p < n_patterns; ++p) {
+        const int m = mmas_per_commit[p];
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t idesc = umma_idesc_f16_f32(128, N);
+            const uint64_t da = umma_smem_desc(a_sm, TC_A_LBO, 128);
+            const uint64_t db = umma_smem_desc(b_sm, (uint32_t)N * 16, 128);
+            const long long t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+                if (elect_one_sync()) {
+                    for (int i = 0; i < m; ++i)
+                        umma_f16_ss(tmem_base, da + (uint32_t)((r * m + i) & 15) * 256u,
+                                    db + (uint32_t)(i & 1) * (uint32_t)(2 * N), idesc, 1);
+                    umma_commit(bar_slab);
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(bar_done);
+            __syncwarp();
+            const long long t1 = clock64();
+            mbar_wait(bar_done, done_phase);
+            const long long t2 = clock64();
+            if (lane == 0) { out[p * 2] = t1 - t0; out[p * 2 + 1] = t2 - t0; }
+        } else if (epi_load) {
+            // competing TMEM reads from the other accumulator half, like a concurrent epilogue
+            uint32_t rr[32];
+            for (int it = 0; it < epi_load; ++it) {
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + (it & 7) * 32, rr);
+                tmem_ld_wait();
+            }
+            if (rr[0] == 0x12345678u) out[63] = rr[1];
+        }
+        done_phase ^= 1;
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace aadff

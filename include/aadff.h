@@ -89,6 +89,12 @@ int aadff_debug_set_desc_swap(int swap);
  * uint64 (zero-filled by the caller), NULL switches tracing off.  See tests/gpu_trace.py.    */
 int aadff_debug_set_trace(void* device_buffer);
 int aadff_debug_trace_entries(void);
+/* What-if timing switches for the fused kernel (results become invalid): bit 0 = skip the weight
+ * copies, bit 1 = skip the operand stores.  0 restores normal operation.                     */
+int aadff_debug_set_flags(int flags);
+/* Issue-cost microbenchmark of tcgen05.mma / tcgen05.commit (see tests/gpu_diag.py mma_timing). */
+int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps, int N, int epi_load,
+                           uint64_t* out_cycles, int device);
 
 #ifdef __cplusplus
 }

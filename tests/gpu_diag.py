@@ -144,6 +144,50 @@ def stage_speed():
                   flush=True)
 
 
+def stage_whatif():
+    """Timing with parts of the kernel switched off (results invalid) to locate the bottleneck."""
+    import torch
+    import aadff_b200
+    from oracle import focal_stack_oracle as orc
+    nat = aadff_b200.native
+    img, dm = orc.synthetic_rgbd(1, 512, 512, seed=1234)
+    foc = -orc.synthetic_focus(dm, 5).cuda() * 1e3
+    img, dep = img.cuda(), -dm.cuda() * 1e3
+    for mode in ("parity", "fast"):
+        lens = _lens(mode=mode)
+        for flags in (0, 1, 2, 3):
+            nat.lib.aadff_debug_set_flags(flags)
+            for _ in range(2):
+                lens.render_stack(img, dep, foc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                lens.render_stack(img, dep, foc)
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"whatif {mode} flags={flags}: {e0.elapsed_time(e1) / 10:.3f} ms", flush=True)
+    nat.lib.aadff_debug_set_flags(0)
+
+
+def stage_mma_timing():
+    import ctypes
+    import numpy as np
+    import aadff_b200
+    nat = aadff_b200.native
+    pats = np.array([1, 2, 4, 6, 8, 16, 64], dtype=np.int32)
+    reps = 16
+    for N in (256, 128):
+        for epi in (0, 4000):
+            out = np.zeros(2 * len(pats), dtype=np.uint64)
+            nat.check(nat.lib.aadff_debug_mma_timing(ctypes.c_void_p(pats.ctypes.data), len(pats), reps, N, epi,
+                                                     ctypes.c_void_p(out.ctypes.data), 0))
+            for i, m in enumerate(pats):
+                tot = int(m) * reps
+                print(f"N={N} epi_load={epi} [{m:2d} MMA + commit] x{reps}: issue {out[2*i]/tot:7.1f} cyc/MMA, "
+                      f"retire {out[2*i+1]/tot:7.1f} cyc/MMA", flush=True)
+
+
 STAGES = {k[6:]: v for k, v in list(globals().items()) if k.startswith("stage_")}
 
 if __name__ == "__main__":
