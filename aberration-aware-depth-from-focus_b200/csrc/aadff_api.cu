@@ -200,7 +200,8 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         const int L = n_layers - 1;
         const int head_bias0 = (int)bias_tc.size();
         bias_tc.resize(head_bias0 + nh_pad, 0.f);
-        for (int n = 0; n < h->kk; ++n) bias_tc[head_bias0 + n] = biases[L][n];
+        // head bias is stored pre-scaled by -log2(e): the kernel evaluates exp(-(acc+b)) as ex2(fma(acc,-log2e,b'))
+        for (int n = 0; n < h->kk; ++n) bias_tc[head_bias0 + n] = -1.4426950408889634f * biases[L][n];
         for (int b = 0; b < n_head_blocks; ++b, ++gi) {
             TcGroup& g = h->groups[gi];
             const int N = std::min(256, nh_pad - 256 * b);
@@ -270,7 +271,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.trace = g_trace.load();
     P.dbg = (uint32_t)g_dbg_flags.load();
     // shared-memory carve-up
-    const uint32_t halo_bytes = (uint32_t)ra.C * (TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 4;
+    const uint32_t halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 16;   // float4 per pixel
     const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES;
     int stages = 4;
     while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     };
     float* s_bias = reinterpret_cast<float*>(smem + P.off_bias);
     float* s_w0 = reinterpret_cast<float*>(smem + P.off_w0);
-    float* s_halo = reinterpret_cast<float*>(smem + P.off_halo);
+    float4* s_halo = reinterpret_cast<float4*>(smem + P.off_halo);   // [HH][48] pixels, channels in .xyzw
     float* s_red = reinterpret_cast<float*>(smem + P.off_red);
     const uint32_t bar0 = sbase + P.off_bar;
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -309,7 +309,6 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const int ks = ra.ks, r = (ks - 1) / 2, kk = P.kk;
         const int HH = TC_TILE_H + ks - 1, HW = TC_TILE_W + ks - 1;
-        const int plane = HH * TC_HALO_PITCH;
         const int tiles_xy = P.tiles_x * P.tiles_y;
         const uint32_t a_row = (uint32_t)row * 16;
         uint32_t afphase = 0;
@@ -374,33 +373,30 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             tr.ev(0x900);                                // layer 0 done
             fetch_dz(tile + gridDim.x, nx_depth, nx_foc);    // prefetch for the next tile
 
-            // ---- halo tile, replicate-clamped (render_psf.py:96), C planes of HH x 48; off the critical
-            //      path: it overlaps the L1 MMAs and is first read by the gather at the end of the tile
+            // The halo tile (replicate-clamped, render_psf.py:96) is only needed by the gather at the end of the
+            // tile: its pixels are fetched one per thread per hidden layer -- the global loads are issued before
+            // the accumulator wait and stored to smem after the layer's epilogue, so they cost no time.
             named_bar_sync(1, TC_EPI_THREADS);           // previous tile's gather is done with halo/red
-            {
-                const float* img_n = ra.img + ((long long)n * ra.Ctot + ra.c0) * ra.H * ra.W;
-                const int per = HH * HW, total = ra.C * per;
-                for (int idx = et; idx < total; idx += 2 * TC_EPI_THREADS) {
-                    const int idx2 = idx + TC_EPI_THREADS;
-                    const int c = idx / per, rem = idx - c * per;
-                    const int yy = rem / HW, xx = rem - yy * HW;
-                    const int gy = min(max(h0 + yy - r, 0), ra.H - 1), gx = min(max(w0 + xx - r, 0), ra.W - 1);
-                    const float v1 = __ldg(img_n + ((long long)c * ra.H + gy) * ra.W + gx);
-                    if (idx2 < total) {
-                        const int c2 = idx2 / per, rem2 = idx2 - c2 * per;
-                        const int yy2 = rem2 / HW, xx2 = rem2 - yy2 * HW;
-                        const int gy2 = min(max(h0 + yy2 - r, 0), ra.H - 1), gx2 = min(max(w0 + xx2 - r, 0), ra.W - 1);
-                        s_halo[c2 * plane + yy2 * TC_HALO_PITCH + xx2] =
-                            __ldg(img_n + ((long long)c2 * ra.H + gy2) * ra.W + gx2);
-                    }
-                    s_halo[c * plane + yy * TC_HALO_PITCH + xx] = v1;
-                }
-            }
+            const float* img_n = ra.img + ((long long)n * ra.Ctot + ra.c0) * ra.H * ra.W;
+            const long long cstride = (long long)ra.H * ra.W;
+            auto halo_fetch = [&](int idx, float4& v) -> int {       // returns the smem slot or -1
+                if (idx >= HH * HW) return -1;
+                const int yy = idx / HW, xx = idx - yy * HW;
+                const int gy = min(max(h0 + yy - r, 0), ra.H - 1), gx = min(max(w0 + xx - r, 0), ra.W - 1);
+                const float* px = img_n + (long long)gy * ra.W + gx;
+                v.x = __ldg(px);
+                v.y = ra.C > 1 ? __ldg(px + cstride) : 0.f;
+                v.z = ra.C > 2 ? __ldg(px + 2 * cstride) : 0.f;
+                v.w = ra.C > 3 ? __ldg(px + 3 * cstride) : 0.f;
+                return yy * TC_HALO_PITCH + xx;
+            };
 
             // ---- hidden layers L1..L9: accumulator -> bias, ReLU, split -> A operand of the next layer.
             //      TMEM reads are software-pipelined one 32-column chunk ahead of the arithmetic.
             for (int gi = 0; gi < P.n_hidden; ++gi) {
                 const int buf = (int)(gcount & 1);
+                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int hslot = halo_fetch(gi * TC_EPI_THREADS + et, hv);
                 tr.ev(0xA00 + gi);                           // start waiting for accumulator gi
                 mbar_wait(bar_accfull(buf), (afphase >> buf) & 1);
                 afphase ^= 1u << buf;
@@ -440,14 +436,20 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_accfree(buf));
+                if (hslot >= 0) s_halo[hslot] = hv;
                 ++gcount;
             }
-
+            for (int idx = P.n_hidden * TC_EPI_THREADS + et; idx < HH * HW; idx += TC_EPI_THREADS) {   // remainder
+                float4 hv;
+                const int hslot = halo_fetch(idx, hv);
+                s_halo[hslot] = hv;
+            }
             named_bar_sync(1, TC_EPI_THREADS);           // halo tile complete (all warps stored their share)
 
             // ---- head blocks: sigmoid, gather from the halo tile (render_psf.py:103-105)
+            //      The bias table holds -log2(e) * bias for the head, so exp(-(acc + b)) is one FFMA + EX2.
             float ssum = 0.f, cacc[TC_MAX_C] = {0.f, 0.f, 0.f, 0.f};
-            const float* hbase = s_halo + ty * TC_HALO_PITCH + tx;
+            const float4* hbase = s_halo + ty * TC_HALO_PITCH + tx;
             for (int gi = P.n_hidden; gi < P.n_groups; ++gi) {
                 const int buf = (int)(gcount & 1);
                 tr.ev(0xA00 + gi);
@@ -466,20 +468,35 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     int off = i * TC_HALO_PITCH + j;
                     const int nvalid = kk - tap_first;     // >= 32 for every group but the padded last one
                     tmem_ld_wait();
-                    // branch-free over the 32 taps so that the MUFU / LDS latencies of different taps overlap
+                    if (nvalid >= 32) {
+                        // branch-free so that the MUFU / LDS latencies of different taps overlap
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        const bool ok = u < nvalid;
-                        const float xl = __uint_as_float(rr[u]) + bias[c32 + u];
-                        float sg = rcp_approx(1.0f + ex2_approx(xl * NEG_LOG2E));
-                        sg = ok ? sg : 0.f;                // padding columns contribute nothing
-                        const int o = ok ? off : 0;        // ... and read a valid halo address
-                        ssum += sg;
+                        for (int u = 0; u < 32; ++u) {
+                            const float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
+                            const float4 px = hbase[off];
+                            ssum += sg;
+                            cacc[0] = fmaf(sg, px.x, cacc[0]);
+                            cacc[1] = fmaf(sg, px.y, cacc[1]);
+                            cacc[2] = fmaf(sg, px.z, cacc[2]);
+                            cacc[3] = fmaf(sg, px.w, cacc[3]);
+                            ++off;
+                            if (++j == ks) { j = 0; off += TC_HALO_PITCH - ks; }
+                        }
+                    } else {
 #pragma unroll
-                        for (int c = 0; c < TC_MAX_C; ++c)
-                            if (c < ra.C) cacc[c] = fmaf(sg, hbase[c * plane + o], cacc[c]);
-                        ++off;
-                        if (++j == ks) { j = 0; off += TC_HALO_PITCH - ks; }
+                        for (int u = 0; u < 32; ++u) {
+                            const bool ok = u < nvalid;    // padding columns contribute nothing and read slot 0
+                            float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
+                            sg = ok ? sg : 0.f;
+                            const float4 px = hbase[ok ? off : 0];
+                            ssum += sg;
+                            cacc[0] = fmaf(sg, px.x, cacc[0]);
+                            cacc[1] = fmaf(sg, px.y, cacc[1]);
+                            cacc[2] = fmaf(sg, px.z, cacc[2]);
+                            cacc[3] = fmaf(sg, px.w, cacc[3]);
+                            ++off;
+                            if (++j == ks) { j = 0; off += TC_HALO_PITCH - ks; }
+                        }
                     }
                 }
                 tc_fence_before_sync();
