@@ -128,6 +128,24 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_
     }
 }
 
+// 8 accumulator columns -> +bias, ReLU, fp16 hi/lo split -> one 16-byte operand row (K-group `kg`)
+__device__ __forceinline__ void epi_group8(const uint32_t* acc, const float* bias, uint32_t a_hi, uint32_t a_lo,
+                                           uint32_t kg, uint32_t a_row, bool need_lo) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + 4);
+    float v[8];
+    v[0] = fmaxf(__uint_as_float(acc[0]) + b0.x, 0.f);
+    v[1] = fmaxf(__uint_as_float(acc[1]) + b0.y, 0.f);
+    v[2] = fmaxf(__uint_as_float(acc[2]) + b0.z, 0.f);
+    v[3] = fmaxf(__uint_as_float(acc[3]) + b0.w, 0.f);
+    v[4] = fmaxf(__uint_as_float(acc[4]) + b1.x, 0.f);
+    v[5] = fmaxf(__uint_as_float(acc[5]) + b1.y, 0.f);
+    v[6] = fmaxf(__uint_as_float(acc[6]) + b1.z, 0.f);
+    v[7] = fmaxf(__uint_as_float(acc[7]) + b1.w, 0.f);
+    const uint32_t off = kg * TC_A_LBO + a_row;
+    store_split8(v, a_hi + off, a_lo + off, need_lo);
+}
+
 // Warp roles.  The hardware warp arbiter favours the HIGHEST warp id on a scheduler, so the two
 // single-thread roles that must react quickly (weight producer, MMA issuer) are the LAST warps of
 // the CTA; with low ids they were starved by the ALU-heavy epilogue warps sharing their scheduler
@@ -157,14 +175,18 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
     auto bar_aready = [&](int j) { return bar0 + 8u * (2 * TC_MAX_STAGES + j); };
-    auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 4 + b); };
-    auto bar_accfree = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 6 + b); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 8));
-    static_assert(8 * (2 * TC_MAX_STAGES + 8) + 4 <= TC_BAR_BYTES, "barrier area too small");
+    auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 8 + b); };
+    auto bar_accfree = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 10 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 12));
+    static_assert(8 * (2 * TC_MAX_STAGES + 12) + 4 <= TC_BAR_BYTES, "barrier area too small");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int j = 0; j < 4; ++j) mbar_init(bar_aready(j), TC_EPI_WARPS);
+        // one per 32-column A chunk.  3-term modes produce chunks 0 and 1 in 16-column steps by all 8 warps
+        // (short first hand-off); every other chunk is written by the 4 warps of one column half.
+        // Fast mode (kslab 2) hands over 64-column chunks written by all 8 warps.
+        for (int j = 0; j < 8; ++j)
+            mbar_init(bar_aready(j), (P.kslab == 2 || j < 2) ? TC_EPI_WARPS : TC_EPI_WARPS / 2);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
         fence_mbar_init();
     }
@@ -237,25 +259,23 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint32_t kstep_b = (2 * gN * 16) >> 4;     // one K=16 step of B: 2 * LBO_B
                 const uint64_t db0 = umma_smem_desc(stage0, gN * 16, 128);
                 uint32_t acc = 0;
-                int prev_stage = -1;     // a stage is released (commit) only after the NEXT stage's MMAs are queued
+                int prev_stage = -1;
                 const int kslab = P.kslab;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
                 for (int it = 0; it < nit; ++it) {
-                    const int kc = it * kslab;                   // first K=32 slab of this stage
-                    if (new_a && (kc & 1) == 0) {
-                        const int j = kc >> 1;
-                        tr.ev(0x300 + j);                        // start waiting for A chunk j
-                        mbar_wait(bar_aready(j), (aphase >> j) & 1);
-                        aphase ^= 1u << j;
-                        tr.ev(0x400 + j);                        // A chunk j ready
-                    }
+                    const int kc = it * kslab;                   // first K=32 slab (= 32-column A chunk) of this stage
                     const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
-                    // ---- hi weight slab(s): Ah*Wh (+ Al*Wh)
-                    tr.ev(0x500 + kc);                           // start waiting for the hi stage
+                    // ---- hi weight stage first (it was prefetched long ago), then the freshly produced A chunk(s)
+                    tr.ev(0x500 + kc);
                     mbar_wait(bar_full(stage), fphase);
-                    tc_fence_after_sync();
                     tr.ev(0x600 + kc);                           // hi stage landed
+                    if (new_a) {                                 // chunk = 32 columns (kslab 1) or 64 (kslab 2)
+                        mbar_wait(bar_aready(it), (aphase >> it) & 1);
+                        aphase ^= 1u << it;
+                        tr.ev(0x400 + kc);                       // A chunk ready
+                    }
+                    tc_fence_after_sync();
                     if (elect_one_sync()) {
                         const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
                         umma_f16_ss(d_tmem, ah, db, idesc, acc);
@@ -268,7 +288,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             umma_f16_ss(d_tmem, al, db, idesc, 1);
                             umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
                         }
-                        if (prev_stage >= 0) umma_commit(bar_empty(prev_stage));
+                        // A commit stalls the issuing thread until the tensor pipe has drained up to it.  With the
+                        // deep fast-mode ring the release of a stage is therefore issued one stage late, behind
+                        // the next stage's MMAs, so the pipe never runs dry; the 3-term ring is too shallow for
+                        // that (64 KB) and has 6 MMAs per K-step to cover the stall instead.
+                        if (kslab == 1) umma_commit(bar_empty(stage));
+                        else if (prev_stage >= 0) umma_commit(bar_empty(prev_stage));
                     }
                     __syncwarp();
                     acc = 1;
@@ -282,16 +307,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
                             umma_f16_ss(d_tmem, ah, db, idesc, 1);
                             umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
-                            umma_commit(bar_empty(prev_stage));
+                            umma_commit(bar_empty(stage));
                         }
                         __syncwarp();
-                        prev_stage = stage;
                         if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
                     }
                 }
                 if (elect_one_sync()) {
-                    umma_commit(bar_accfull(buf));               // the epilogue is waiting on this one
-                    umma_commit(bar_empty(prev_stage));
+                    umma_commit(bar_accfull(buf));
+                    if (kslab == 2) umma_commit(bar_empty(prev_stage));
                 }
                 __syncwarp();
                 tr.ev(0x700 + gi);                               // group fully issued
@@ -315,6 +339,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         unsigned long long gcount = 0;
         TcTrace<TRACE> tr; tr.init((lane == 0 && (e == 0 || e == 7)) ? P.trace : nullptr, e == 0 ? 2 : 3);
         const float NEG_LOG2E = -1.4426950408889634f;
+        const bool fine = P.kslab == 1;         // 16-column first hand-offs (3-term modes)
 
         // tile -> (image n, slice s, tile origin); depth / focus of this thread's pixel are fetched
         // one tile ahead so that layer 0 (the head of the serial chain) never waits on HBM
@@ -354,21 +379,27 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const bool need_lo = P.g[0].terms == 3;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    // K-group (8 features) computed in this step: a contiguous quarter in fast mode, half of
+                    // chunk 0 and half of chunk 1 when the chunks are shared by all warps (fine hand-off)
+                    const int kg = fine ? ((i >> 1) * 4 + 2 * hh + (i & 1)) : (hh * 4 + i);
                     float v[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int f = hh * 32 + i * 8 + u;
+                        const int f = kg * 8 + u;
                         const float4 wv = *reinterpret_cast<const float4*>(s_w0 + f * 4);
                         float a = s_w0[256 + f];
                         a = fmaf(wv.x, x, a); a = fmaf(wv.y, y, a); a = fmaf(wv.z, z, a); a = fmaf(wv.w, fz, a);
                         v[u] = fmaxf(a, 0.f);
                     }
-                    const uint32_t off = (uint32_t)(hh * 4 + i) * TC_A_LBO + a_row;
+                    const uint32_t off = (uint32_t)kg * TC_A_LBO + a_row;
                     store_split8(v, a_hi + off, a_lo + off, need_lo);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_aready(0));
+                if (lane == 0) {
+                    if (fine) { mbar_arrive(bar_aready(0)); mbar_arrive(bar_aready(1)); }
+                    else mbar_arrive(bar_aready(0));
+                }
             }
             tr.ev(0x900);                                // layer 0 done
             fetch_dz(tile + gridDim.x, nx_depth, nx_foc);    // prefetch for the next tile
@@ -403,35 +434,40 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 tc_fence_after_sync();
                 tr.ev(0xB00 + gi);                           // accumulator gi complete
                 const bool need_lo = P.g[gi + 1].terms == 3;
-                const float* bias = s_bias + P.g[gi].bias_off + hh * 32;
-                const uint32_t t_col = t_lane + buf * 256 + hh * 32;
-                uint32_t rr[2][32];
-                tmem_ld32(t_col, rr[0]);
+                const float* bias = s_bias + P.g[gi].bias_off;
+                const uint32_t t_acc = t_lane + buf * 256;
+                uint32_t rr[2][32], rf[2][16];
+                if (fine) {
+                    tmem_ld16(t_acc + hh * 16, rf[0]);          // my 16 columns of chunk 0 ...
+                    tmem_ld16(t_acc + 32 + hh * 16, rf[1]);     // ... and of chunk 1
+                } else {
+                    tmem_ld32(t_acc + hh * 32, rr[0]);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     tmem_ld_wait();
-                    if (j < 3) tmem_ld32(t_col + (j + 1) * 64, rr[(j + 1) & 1]);
-                    const uint32_t(&cur)[32] = rr[j & 1];
+                    if (j < 3) tmem_ld32(t_acc + (j + 1) * 64 + hh * 32, rr[(j + 1) & 1]);
+                    if (j == 0 && fine) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 64 + i * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 64 + i * 8 + 4);
-                        float v[8];
-                        v[0] = fmaxf(__uint_as_float(cur[i * 8 + 0]) + b0.x, 0.f);
-                        v[1] = fmaxf(__uint_as_float(cur[i * 8 + 1]) + b0.y, 0.f);
-                        v[2] = fmaxf(__uint_as_float(cur[i * 8 + 2]) + b0.z, 0.f);
-                        v[3] = fmaxf(__uint_as_float(cur[i * 8 + 3]) + b0.w, 0.f);
-                        v[4] = fmaxf(__uint_as_float(cur[i * 8 + 4]) + b1.x, 0.f);
-                        v[5] = fmaxf(__uint_as_float(cur[i * 8 + 5]) + b1.y, 0.f);
-                        v[6] = fmaxf(__uint_as_float(cur[i * 8 + 6]) + b1.z, 0.f);
-                        v[7] = fmaxf(__uint_as_float(cur[i * 8 + 7]) + b1.w, 0.f);
-                        const uint32_t off = (uint32_t)(j * 8 + hh * 4 + i) * TC_A_LBO + a_row;
-                        if (!(P.dbg & 2) || v[0] == 123.456f) store_split8(v, a_hi + off, a_lo + off, need_lo);
+                        for (int c = 0; c < 2; ++c) {
+                            const int col = c * 32 + hh * 16;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                epi_group8(&rf[c][i * 8], bias + col + i * 8, a_hi, a_lo, col / 8 + i, a_row, need_lo);
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_aready(c));
+                        }
+                    } else {
+                        const int col = j * 64 + hh * 32;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            epi_group8(&rr[j & 1][i * 8], bias + col + i * 8, a_hi, a_lo, col / 8 + i, a_row, need_lo);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_aready(fine ? 2 * j + hh : j));
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_aready(j));
-                    tr.ev(0xC00 + j);                        // chunk j handed to the MMA warp
+                    tr.ev(0xC00 + j);                        // columns of 64-group j handed to the MMA warp
                 }
                 tc_fence_before_sync();
                 __syncwarp();
