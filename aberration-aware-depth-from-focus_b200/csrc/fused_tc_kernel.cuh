@@ -258,27 +258,31 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint32_t idesc = umma_idesc_f16_f32(TC_M, gN);
                 const uint32_t kstep_b = (2 * gN * 16) >> 4;     // one K=16 step of B: 2 * LBO_B
                 const uint64_t db0 = umma_smem_desc(stage0, gN * 16, 128);
-                uint32_t acc = 0;
-                int prev_stage = -1;
+                // Issue loop, software-pipelined by one step: the barrier waits of step it+1 (~90 cycles each even
+                // when already complete) are performed after the MMAs of step it are queued and BEFORE the commit
+                // that drains the pipe, so they overlap MMA execution instead of idling the tensor pipe.
                 const int kslab = P.kslab;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
+                bool pre_waited = false;
                 for (int it = 0; it < nit; ++it) {
-                    const int kc = it * kslab;                   // first K=32 slab (= 32-column A chunk) of this stage
+                    const int kc = it * kslab;                   // first K=32 slab of this step
                     const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
-                    // ---- hi weight stage first (it was prefetched long ago), then the freshly produced A chunk(s)
-                    tr.ev(0x500 + kc);
-                    mbar_wait(bar_full(stage), fphase);
-                    tr.ev(0x600 + kc);                           // hi stage landed
-                    if (new_a) {                                 // chunk = 32 columns (kslab 1) or 64 (kslab 2)
-                        mbar_wait(bar_aready(it), (aphase >> it) & 1);
-                        aphase ^= 1u << it;
-                        tr.ev(0x400 + kc);                       // A chunk ready
+                    if (!pre_waited) {
+                        tr.ev(0x500 + kc);
+                        mbar_wait(bar_full(stage), fphase);      // hi weight stage (prefetched long ago)
+                        tr.ev(0x600 + kc);
+                        if (new_a) {                             // A chunk: 32 columns (kslab 1) or 64 (kslab 2)
+                            mbar_wait(bar_aready(it), (aphase >> it) & 1);
+                            aphase ^= 1u << it;
+                            tr.ev(0x400 + kc);
+                        }
                     }
                     tc_fence_after_sync();
+                    const int hi_stage = stage;
                     if (elect_one_sync()) {
-                        const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
-                        umma_f16_ss(d_tmem, ah, db, idesc, acc);
+                        const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
+                        umma_f16_ss(d_tmem, ah, db, idesc, it != 0);
                         umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
                         if (kslab == 2) {
                             umma_f16_ss(d_tmem, ah + 2 * KSTEP_A, db + STAGE_STEP, idesc, 1);
@@ -287,37 +291,46 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         if (three) {
                             umma_f16_ss(d_tmem, al, db, idesc, 1);
                             umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
-                        }
-                        // A commit stalls the issuing thread until the tensor pipe has drained up to it.  With the
-                        // deep fast-mode ring the release of a stage is therefore issued one stage late, behind
-                        // the next stage's MMAs, so the pipe never runs dry; the 3-term ring is too shallow for
-                        // that (64 KB) and has 6 MMAs per K-step to cover the stall instead.
-                        if (kslab == 1) umma_commit(bar_empty(stage));
-                        else if (prev_stage >= 0) umma_commit(bar_empty(prev_stage));
+                            umma_commit(bar_empty(hi_stage));    // release the hi stage early: the 3-term ring is
+                        }                                        // only 64 KB deep and 4 MMAs cover the stall
                     }
                     __syncwarp();
-                    acc = 1;
-                    prev_stage = stage;
                     if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                    int last_stage = hi_stage;
                     if (three) {
                         // ---- lo weight slab: Ah*Wl
                         mbar_wait(bar_full(stage), fphase);
                         tc_fence_after_sync();
+                        last_stage = stage;
                         if (elect_one_sync()) {
-                            const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
+                            const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(last_stage) & 0x3FFFFu) >> 4);
                             umma_f16_ss(d_tmem, ah, db, idesc, 1);
                             umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
-                            umma_commit(bar_empty(stage));
                         }
                         __syncwarp();
                         if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
                     }
+                    // ---- waits of the next step, while the MMAs above execute
+                    //      (fast mode only: in the 3-term modes the MMA warp runs ahead of the epilogue for the first
+                    //      chunks, and waiting for the next A chunk here would hold back the stage release)
+                    pre_waited = false;
+                    if (!three && it + 1 < nit) {
+                        tr.ev(0x500 + kc + kslab);
+                        mbar_wait(bar_full(stage), fphase);
+                        if (new_a) {
+                            mbar_wait(bar_aready(it + 1), (aphase >> (it + 1)) & 1);
+                            aphase ^= 1u << (it + 1);
+                        }
+                        tr.ev(0x400 + kc + kslab);
+                        pre_waited = true;
+                    }
+                    // ---- now the draining commit(s)
+                    if (elect_one_sync()) {
+                        if (it + 1 == nit) umma_commit(bar_accfull(buf));   // the epilogue is waiting for this one
+                        umma_commit(bar_empty(last_stage));
+                    }
+                    __syncwarp();
                 }
-                if (elect_one_sync()) {
-                    umma_commit(bar_accfull(buf));
-                    if (kslab == 2) umma_commit(bar_empty(prev_stage));
-                }
-                __syncwarp();
                 tr.ev(0x700 + gi);                               // group fully issued
                 ++gcount;
             }
@@ -363,46 +376,50 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         float nx_depth = 0.f, nx_foc = 0.f;
         fetch_dz(blockIdx.x, nx_depth, nx_foc);
 
+        // ---- layer 0 (4 -> 64) in fp32 for tile `t`: (x, y, z, foc_z) -> 64 features -> A operand of L1.
+        //      Runs one tile AHEAD: right after the previous tile's last head block has retired (the A buffer is
+        //      free again) and BEFORE that tile's gather, so the L1 MMAs of tile t overlap the gather of tile t-1.
+        auto layer0 = [&](long long t) {
+            int n, s, h0, w0;
+            tile_coords(t, n, s, h0, w0);
+            const float x = coord_x(min(w0 + tx, ra.W - 1), ra.W, ra.step_x);
+            const float y = coord_y(min(h0 + ty, ra.H - 1), ra.H, ra.step_y);
+            const float z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
+            const float fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
+            const bool need_lo = P.g[0].terms == 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // K-group (8 features) computed in this step: a contiguous quarter in fast mode, half of
+                // chunk 0 and half of chunk 1 when the chunks are shared by all warps (fine hand-off)
+                const int kg = fine ? ((i >> 1) * 4 + 2 * hh + (i & 1)) : (hh * 4 + i);
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int f = kg * 8 + u;
+                    const float4 wv = *reinterpret_cast<const float4*>(s_w0 + f * 4);
+                    float a = s_w0[256 + f];
+                    a = fmaf(wv.x, x, a); a = fmaf(wv.y, y, a); a = fmaf(wv.z, z, a); a = fmaf(wv.w, fz, a);
+                    v[u] = fmaxf(a, 0.f);
+                }
+                const uint32_t off = (uint32_t)kg * TC_A_LBO + a_row;
+                store_split8(v, a_hi + off, a_lo + off, need_lo);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (fine) { mbar_arrive(bar_aready(0)); mbar_arrive(bar_aready(1)); }
+                else mbar_arrive(bar_aready(0));
+            }
+        };
+        if ((long long)blockIdx.x < P.n_tiles) layer0(blockIdx.x);
+
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             int n, s, h0, w0;
             tile_coords(tile, n, s, h0, w0);
             const int h = h0 + ty, w = w0 + tx;
             const bool valid = (h < ra.H) && (w < ra.W);
-            tr.ev(0x800);                                // tile start
-
-            // ---- layer 0 (4 -> 64) in fp32: this thread computes features [32*hh, 32*hh+32) of its pixel
-            {
-                const float x = coord_x(min(w, ra.W - 1), ra.W, ra.step_x);
-                const float y = coord_y(min(h, ra.H - 1), ra.H, ra.step_y);
-                const float z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
-                const float fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
-                const bool need_lo = P.g[0].terms == 3;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // K-group (8 features) computed in this step: a contiguous quarter in fast mode, half of
-                    // chunk 0 and half of chunk 1 when the chunks are shared by all warps (fine hand-off)
-                    const int kg = fine ? ((i >> 1) * 4 + 2 * hh + (i & 1)) : (hh * 4 + i);
-                    float v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int f = kg * 8 + u;
-                        const float4 wv = *reinterpret_cast<const float4*>(s_w0 + f * 4);
-                        float a = s_w0[256 + f];
-                        a = fmaf(wv.x, x, a); a = fmaf(wv.y, y, a); a = fmaf(wv.z, z, a); a = fmaf(wv.w, fz, a);
-                        v[u] = fmaxf(a, 0.f);
-                    }
-                    const uint32_t off = (uint32_t)kg * TC_A_LBO + a_row;
-                    store_split8(v, a_hi + off, a_lo + off, need_lo);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    if (fine) { mbar_arrive(bar_aready(0)); mbar_arrive(bar_aready(1)); }
-                    else mbar_arrive(bar_aready(0));
-                }
-            }
-            tr.ev(0x900);                                // layer 0 done
-            fetch_dz(tile + gridDim.x, nx_depth, nx_foc);    // prefetch for the next tile
+            tr.ev(0x800);                                // tile start (its layer 0 is already done)
+            fetch_dz(tile + gridDim.x, nx_depth, nx_foc);    // depth / focus of the next tile, used by layer0 below
 
             // The halo tile (replicate-clamped, render_psf.py:96) is only needed by the gather at the end of the
             // tile: its pixels are fetched one per thread per hidden layer -- the global loads are issued before
@@ -493,6 +510,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 afphase ^= 1u << buf;
                 tc_fence_after_sync();
                 tr.ev(0xB00 + gi);
+                if (gi == P.n_groups - 1 && tile + gridDim.x < P.n_tiles) {
+                    layer0(tile + gridDim.x);            // every MMA that read this tile's A operand has retired
+                    tr.ev(0x900);
+                }
                 const int gN = P.g[gi].N, gtap0 = P.g[gi].tap0;
                 const float* bias = s_bias + P.g[gi].bias_off;
 #pragma unroll 1
