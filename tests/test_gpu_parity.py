@@ -291,3 +291,16 @@ def test_c4_large_kernel_full_frame(lens31):
     assert float((out[:, :, :1] - ref).abs().max()) < TOL["parity"]
     const = lens31.render_stack(torch.full_like(img, 0.25), dep, foc[:, 1:], mode="parity")
     assert float((const - 0.25).abs().max()) < 2e-6
+
+
+def test_multi_gpu_sharded_render_matches_single_gpu():
+    """2 ranks over NCCL: shares rendered per rank, all_gathered, bit-identical to one GPU (skips on 1 GPU)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613",
+                          os.path.join(root, "tests", "gpu_multi_verify.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MULTI_GPU_VERIFY PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
