@@ -394,6 +394,32 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int kk = ks * ks;
+    int P = 32, nbuf = 1;
+    while (P > 4 && P * kk * 4 > GS_BUF_BYTES) P >>= 1;
+    // (two half-size chunks per warp -- nbuf = 2 -- measured slower: 16-pixel chunks leave the one-lane-per-pixel
+    //  fast path; the kernel keeps the option, the host does not use it)
+    const bool stream_ok = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(psf) % 16 == 0) && (P * kk * 4 <= GS_BUF_BYTES);
+    if (stream_ok) {
+        // HBM-streaming path: cp.async.bulk PSF chunks, smem halo tile
+        const int HH = GS_TILE_H + ks - 1, pitch = (GS_TILE_W + ks - 1) | 1;
+        const int smem = GS_TILE_H * GS_BUF_BYTES + GS_MAXC * HH * pitch * 4 + 16 * GS_TILE_H;
+        static std::atomic<int> attr_smem{0};
+        if (attr_smem.load() < smem) {
+            CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_smem.store(smem);
+        }
+        const long long tiles = (long long)N * ((H + GS_TILE_H - 1) / GS_TILE_H) * ((W + GS_TILE_W - 1) / GS_TILE_W);
+        const int grid = (int)std::min<long long>(tiles, sms);
+        for (int c0 = 0; c0 < C; c0 += GS_MAXC) {
+            local_psf_stream_kernel<<<grid, GS_TILE_H * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0,
+                                                                        std::min(GS_MAXC, C - c0), P, nbuf);
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+        }
+        return AADFF_OK;
+    }
     static std::atomic<bool> attr_set{false};
     const int smem = GATHER_WARPS * 32 * (GATHER_TT + 1) * (int)sizeof(float);
     if (!attr_set.exchange(true))
@@ -401,8 +427,8 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     const long long items = (long long)N * H * ((W + 31) / 32);
     const int grid = (int)std::min<long long>((items + GATHER_WARPS - 1) / GATHER_WARPS, (long long)sms * 3);
     for (int c0 = 0; c0 < C; c0 += GATHER_MAXC) {
-        local_psf_render_kernel<<<grid, GATHER_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-            img, psf, out, N, C, H, W, ks, c0, std::min(GATHER_MAXC, C - c0));
+        local_psf_render_kernel<<<grid, GATHER_WARPS * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0,
+                                                                       std::min(GATHER_MAXC, C - c0));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }

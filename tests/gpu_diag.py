@@ -188,6 +188,34 @@ def stage_mma_timing():
                       f"retire {out[2*i+1]/tot:7.1f} cyc/MMA", flush=True)
 
 
+def stage_rows():
+    """Throughput of the stand-alone rows: local_psf_render (HBM-bound on the PSF read) and pred."""
+    import torch
+    import aadff_b200
+    def timeit(fn, iters=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    for (N, H, W, ks) in [(1, 480, 640, 11), (4, 512, 512, 11), (1, 540, 960, 31)]:
+        img = torch.rand(N, 3, H, W, device="cuda")
+        psf = torch.rand(N, H, W, ks, ks, device="cuda")
+        ms = timeit(lambda: aadff_b200.local_psf_render(img, psf, ks))
+        px = N * H * W
+        gb = px * (ks * ks * 4 + 24) / 1e9
+        print(f"gather N{N} {H}x{W} k{ks}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  {gb / ms * 1e3:.0f} GB/s", flush=True)
+    lens = _lens(mode="parity")
+    inp = torch.rand(1 << 20, 4, device="cuda")
+    ms = timeit(lambda: lens.pred(inp), iters=3)
+    print(f"pred M=1Mi k11 (fp32 kernel): {ms:.3f} ms  {inp.shape[0] / ms / 1e3:.1f} Mprobes/s", flush=True)
+
+
 STAGES = {k[6:]: v for k, v in list(globals().items()) if k.startswith("stage_")}
 
 if __name__ == "__main__":
