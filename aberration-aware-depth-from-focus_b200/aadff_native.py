@@ -47,10 +47,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def _header_symbols():
+    import re
+    with open(HEADER) as f:
+        return sorted(set(re.findall(r"\b(aadff_[a-z0-9_]+)\s*\(", f.read())))
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         build()
     lib = ctypes.CDLL(LIB_PATH)
+    if any(not hasattr(lib, name) for name in _header_symbols()):     # stale binary: rebuild once
+        import _ctypes
+        _ctypes.dlclose(lib._handle)
+        build(force=True)
+        lib = ctypes.CDLL(LIB_PATH)
     c_f32p = ctypes.POINTER(ctypes.c_float)
     lib.aadff_version.restype = ctypes.c_int
     lib.aadff_last_error.restype = ctypes.c_char_p
@@ -68,9 +79,11 @@ def _load() -> ctypes.CDLL:
                                           ctypes.c_void_p]
     lib.aadff_local_psf_render_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     lib.aadff_debug_umma_gemm.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3
+    lib.aadff_thinlens_render_f32.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_float] * 5 + \
+                                             [ctypes.c_int, ctypes.c_void_p]
     lib.aadff_debug_set_desc_swap.argtypes = [ctypes.c_int]
     for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32",
-               "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_local_psf_render_f32",
+               "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_local_psf_render_f32", "aadff_thinlens_render_f32",
                "aadff_debug_umma_gemm", "aadff_debug_set_desc_swap"):
         getattr(lib, fn).restype = ctypes.c_int
     return lib
@@ -90,10 +103,7 @@ def check(rc: int) -> None:
 
 def exported_symbols():
     """Names declared in include/aadff.h (used by the CPU test that checks the library exports them)."""
-    import re
-    with open(HEADER) as f:
-        text = f.read()
-    return sorted(set(re.findall(r"\b(aadff_[a-z0-9_]+)\s*\(", text)))
+    return _header_symbols()
 
 
 class NativePSFNet:

@@ -14,6 +14,7 @@
 #include "fused_tc_kernel.cuh"
 #include "gather_kernel.cuh"
 #include "mlp_fp32_kernel.cuh"
+#include "thinlens_kernel.cuh"
 
 using namespace aadff;
 
@@ -429,6 +430,43 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     for (int c0 = 0; c0 < C; c0 += GATHER_MAXC) {
         local_psf_render_kernel<<<grid, GATHER_WARPS * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0,
                                                                        std::min(GATHER_MAXC, C - c0));
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return AADFF_OK;
+}
+
+int aadff_thinlens_render_f32(const float* img, const float* depth, const float* foc, float* out, int N, int C, int H,
+                              int W, int ks, float foc_len, float fnum, float pixel_size, float d_lo, float d_hi,
+                              int flip_sign, void* stream) {
+    if (!img || !depth || !foc || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (N < 0 || C < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (ks < 1 || (ks % 2) == 0) return fail(AADFF_E_INVALID, "kernel size must be odd and positive");
+    if (!(fnum > 0.f) || !(pixel_size > 0.f) || !(d_hi > d_lo)) return fail(AADFF_E_INVALID, "bad lens parameters");
+    if (N == 0) return AADFF_OK;
+    int dev = 0, sms = 0, optin = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    ThinLensArgs a{};
+    a.img = img; a.depth = depth; a.foc = foc; a.out = out;
+    a.N = N; a.C = C; a.H = H; a.W = W; a.ks = ks;
+    a.k1 = (float)((double)foc_len / (double)fnum);
+    a.foc_len = foc_len; a.ps = pixel_size; a.d_lo = d_lo; a.d_hi = d_hi; a.flip = flip_sign ? 1 : 0;
+    const int HH = TL_TILE_H + ks - 1, pitch = (TL_TILE_W + ks - 1) | 1;
+    const int smem = TL_MAXC * HH * pitch * 4;
+    if (smem > optin) return fail(AADFF_E_UNSUPPORTED, "kernel size too large for the shared-memory halo tile");
+    static std::atomic<int> attr_smem{0};
+    if (attr_smem.load() < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(thinlens_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem.store(smem);
+    }
+    const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + TL_TILE_W - 1) / TL_TILE_W);
+    const int grid = (int)std::min<long long>(tiles, (long long)sms * 4);
+    for (int c0 = 0; c0 < C; c0 += TL_MAXC) {
+        a.c0 = c0;
+        a.cn = std::min(TL_MAXC, C - c0);
+        thinlens_render_kernel<<<grid, TL_TILE_H * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }

@@ -210,19 +210,40 @@ class ThinLens(nn.Module):
 
     @torch.no_grad()
     def render(self, img, depth, foc_dist):
-        """img [N,C,H,W], depth [N,1,H,W], foc_dist [N] -> [N,C,H,W]."""
+        """img [N,C,H,W], depth [N,1,H,W], foc_dist [N] -> [N,C,H,W] (fused CUDA kernel: coc -> clipped
+        Gaussian PSF -> gather; the PSF tensor of the reference is never materialised)."""
         if img.dim() != 4:
             raise ValueError("ThinLens.render expects a [N,C,H,W] image")
-        ks = self.kernel_size
-        device = img.device
+        if not img.is_cuda:
+            raise RuntimeError("ThinLens.render: CUDA tensors required (no CPU fallback in this build)")
         N, C, H, W = img.shape
+        img = img.detach().contiguous().float()
+        dep = depth.detach().to(img.device, torch.float32).reshape(N, H, W).contiguous()
+        foc = torch.as_tensor(foc_dist).detach().to(img.device, torch.float32).reshape(N).contiguous()
+        out = torch.empty_like(img)
+        if out.numel() == 0:
+            return out
+        flip = int(bool((dep < 0).any()))          # the reference's data-dependent sign convention (psfnet.py:504)
+        with torch.cuda.device(img.device):
+            _nat.check(_nat.lib.aadff_thinlens_render_f32(
+                img.data_ptr(), dep.data_ptr(), foc.data_ptr(), out.data_ptr(), N, C, H, W, int(self.kernel_size),
+                float(self.foc_len), float(self.fnum), float(self.ps), float(self.d_min), float(self.d_max), flip,
+                torch.cuda.current_stream().cuda_stream))
+        return out
+
+    @torch.no_grad()
+    def psf(self, depth, foc_dist):
+        """The per-pixel thin-lens PSFs [N,H,W,ks,ks] as the reference builds them (psfnet.py:549-566); kept
+        for inspection / for callers that want to feed local_psf_render themselves."""
+        ks = self.kernel_size
+        device = depth.device
+        N, _, H, W = depth.shape
         foc = foc_dist.to(device).view(N, 1, 1, 1).expand(N, 1, H, W)
         lin = torch.linspace(-ks / 2 + 1 / 2, ks / 2 - 1 / 2, ks)
         x, y = torch.meshgrid(lin, torch.linspace(ks / 2 - 1 / 2, -ks / 2 + 1 / 2, ks), indexing='xy')
         x, y = x.to(device), y.to(device)
-        radius = (self.coc(depth.to(device), foc).squeeze(1) / 2)[..., None, None]
+        radius = (self.coc(depth, foc).squeeze(1) / 2)[..., None, None]
         r2 = x ** 2 + y ** 2
         psf = torch.exp(-r2 / 2 / radius ** 2) / (2 * np.pi * radius ** 2)
         psf = psf * (r2 < radius ** 2)
-        psf = psf / psf.sum((-1, -2), keepdim=True)
-        return local_psf_render(img, psf, ks)
+        return psf / psf.sum((-1, -2), keepdim=True)

@@ -43,12 +43,27 @@ def flops_per_pixel(ks):
 
 
 def load_peaks():
+    """(burst bf16 TFLOP/s, sustained bf16 TFLOP/s, HBM GB/s, source)"""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", 0.0)), float(p["hbm_gbs"]), "measured"
     except Exception:
-        return 1590.0, 6650.0, "fallback"
+        return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def executed_mma_flops_per_pixel(ks, mode):
+    """MMA FLOPs the kernel really issues per pixel*slice: layers L1..L10 on tensor cores (layer 0 runs on CUDA
+    cores), head padded to a multiple of 16 columns, times the number of fp16 terms per layer."""
+    head = (ks * ks + 15) // 16 * 16
+    per_layer = [64 * 256] + [256 * 256] * 8 + [256 * head]
+    terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "fp32": [0] * 10}[mode]
+    return 2 * sum(t * m for t, m in zip(terms, per_layer))
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` captures
+# (profiles/r01_ncu_summary.md); the 15.7 MB output of c2 was still L2-resident when the capture ended.
+NCU_TRAFFIC_BYTES = {("c2", "parity"): 6.57e6, ("c2", "fast"): 5.43e6}
 
 
 def weights_for(ks):
@@ -251,9 +266,10 @@ def run_ours(args):
                            "dtype": DTYPES[mode]}
 
     if rank == 0:
-        peak_tf, peak_hbm, peak_src = load_peaks()
+        peak_tf, peak_tf_sus, peak_hbm, peak_src = load_peaks()
         ms_kernel = statistics.mean(times)
         achieved = flops_per_pixel(ks) * units / (ms_kernel * 1e-3) / 1e12
+        executed = executed_mma_flops_per_pixel(ks, args.mode) * units / (ms_kernel * 1e-3) / 1e12
         line = {
             "metric": "focal-stack Mpix*slices/s (fused PSFNet+PSF render)", "value": value, "unit": "Mpix*slices/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -269,7 +285,11 @@ def run_ours(args):
                     "max_abs_vs_device_path": same},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16 burst",
+                         "frac": achieved / peak_tf, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.mode)),
+                         "peak_source": f"{peak_src} bf16 burst",
+                         "executed_mma_tflops": executed, "executed_frac_of_burst_peak": executed / peak_tf,
+                         "executed_frac_of_sustained_peak": (executed / peak_tf_sus) if peak_tf_sus else None,
+                         "algorithmic_bytes_per_launch": int(units * (12 + 16 / S)),
                          "kernel": "fused_psfnet_render_kernel", "kernel_ms": ms_kernel,
                          "algorithmic_flops_per_pixel_slice": flops_per_pixel(ks),
                          "executed_mma_terms": {"parity": 3, "fast": 1, "mixed": "3 for L1-L3, 1 after", "fp32": 0}[args.mode]},

@@ -77,6 +77,15 @@ int aadff_psfnet_pred_f32(aadff_psfnet_t net, const float* inp, float* psf, int6
 int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, int N, int C, int H, int W, int ks,
                                void* stream);
 
+/* Replaces ThinLens.render + ThinLens.coc (deeplens/psfnet.py:503-570), the thin-lens baseline of the paper:
+ * circle of confusion -> clipped Gaussian PSF (sigma = coc/2) -> normalise -> per-pixel gather, fused (no PSF
+ * tensor in memory).  img [N,C,H,W], depth [N,H,W] mm, foc [N] mm, out [N,C,H,W]; device pointers.
+ * pixel_size = sensor_size[0] / sensor_res[0] [mm]; d_lo/d_hi = 200 / 20000 mm (ThinLens.d_min / d_max);
+ * flip_sign = 1 negates depth and foc first, which is what the reference does when any depth is negative.   */
+int aadff_thinlens_render_f32(const float* img, const float* depth, const float* foc, float* out, int N, int C, int H,
+                              int W, int ks, float foc_len, float fnum, float pixel_size, float d_lo, float d_hi,
+                              int flip_sign, void* stream);
+
 /* Number of kernels launched by this library in the calling process (bench bookkeeping).      */
 int64_t aadff_launch_count(void);
 

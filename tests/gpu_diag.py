@@ -210,6 +210,14 @@ def stage_rows():
         px = N * H * W
         gb = px * (ks * ks * 4 + 24) / 1e9
         print(f"gather N{N} {H}x{W} k{ks}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  {gb / ms * 1e3:.0f} GB/s", flush=True)
+    from deeplens.psfnet import ThinLens
+    for (N, H, W, ks) in [(4, 512, 512, 11), (1, 1080, 1920, 31)]:
+        tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=ks, sensor_size=[36.0, 24.0], sensor_res=(H, W)).to("cuda")
+        img = torch.rand(N, 3, H, W, device="cuda")
+        dep = -(300 + 5000 * torch.rand(N, 1, H, W, device="cuda"))
+        foc = -(500 + 3000 * torch.rand(N, device="cuda"))
+        ms = timeit(lambda: tl.render(img, dep, foc))
+        print(f"thinlens N{N} {H}x{W} k{ks}: {ms:.3f} ms  {N * H * W / ms / 1e3:.1f} Mpix/s", flush=True)
     lens = _lens(mode="parity")
     inp = torch.rand(1 << 20, 4, device="cuda")
     ms = timeit(lambda: lens.pred(inp), iters=3)

@@ -173,8 +173,20 @@ def test_thinlens_and_focus_golden(pkg):
     g = load_golden("kat_h_thinlens.npz")
     tl = ThinLens(foc_len=float(g["foc_len"]), fnum=float(g["fnum"]), kernel_size=11,
                   sensor_size=[float(v) for v in g["sensor_size"]], sensor_res=(40, 56)).to("cuda")
-    out = tl.render(T(g["img"]).cuda(), -T(g["depth_m"]).cuda() * 1e3, T(g["foc"]).cuda())
+    out = tl.render(T(g["img"]).cuda(), -T(g["depth_m"]).cuda() * 1e3, T(g["foc"]).cuda())      # fused kernel
     assert maxabs(out, T(g["out"])) < 5e-6
+    # the reference's two-step formulation (materialised PSFs + gather kernel) agrees with the fused kernel
+    from deeplens.render_psf import local_psf_render
+    psf = tl.psf(-T(g["depth_m"]).cuda() * 1e3, T(g["foc"]).cuda())
+    assert maxabs(local_psf_render(T(g["img"]).cuda(), psf, 11), T(g["out"])) < 5e-6
+    # positive-depth convention (no sign flip), odd sizes, 1 and 5 channels
+    gen = torch.Generator().manual_seed(5)
+    for (N, C, H, W) in [(1, 1, 9, 13), (2, 5, 17, 40)]:
+        img = torch.rand(N, C, H, W, generator=gen)
+        dep = 300 + 6000 * torch.rand(N, 1, H, W, generator=gen)
+        foc = 500 + 3000 * torch.rand(N, generator=gen)
+        ref = orc.thinlens_render(img, dep, foc, 11, float(g["foc_len"]), float(g["fnum"]), tl.ps)
+        assert maxabs(tl.render(img.cuda(), dep.cuda(), foc.cuda()), ref) < 5e-6
     g = load_golden("kat_f_select_focus.npz")
     # on the GPU torch divides by a Python scalar as multiply-by-reciprocal: 1 ulp from the CPU golden
     assert torch.allclose(select_focus_dist(T(g["depth_m"]).cuda(), 5).cpu(), T(g["out"]), rtol=3e-7, atol=0)
