@@ -263,7 +263,11 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.kk = h->kk;
     for (int i = 0; i < h->n_groups; ++i) {
         P.g[i] = h->groups[i];
-        P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1 : (mode == AADFF_MODE_MIXED && i >= 3) ? 1 : 3;
+        const bool hidden = i < h->n_hidden;
+        P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1
+                       : (mode == AADFF_MODE_MIXED && i >= 3) ? 1
+                       : (mode == AADFF_MODE_ECON && hidden && i >= 4) ? 2     // L5..L9: weights rounded to fp16
+                       : 3;
     }
     P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
     P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
@@ -278,7 +282,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;
     if (stages < 2) return fail(AADFF_E_UNSUPPORTED, "shared memory budget exceeded for this kernel size / channel count");
     bool any_lo = false;
-    for (int i = 0; i < h->n_groups; ++i) any_lo |= (P.g[i].terms == 3);
+    for (int i = 0; i < h->n_groups; ++i) any_lo |= (P.g[i].terms >= 2);
     P.off_stage = 2 * TC_A_PART_BYTES;
     P.off_bias = P.off_stage + stages * TC_STAGE_BYTES;
     P.off_w0 = P.off_bias + (uint32_t)h->n_bias * 4;
@@ -305,7 +309,7 @@ int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* dept
                            float d_max, int mode, void* stream) {
     if (!h || !img || !depth || !foc || !out || !out_strides) return fail(AADFF_E_INVALID, "null argument");
     if (N < 0 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
-    if (mode < 0 || mode > 3) return fail(AADFF_E_INVALID, "unknown mode");
+    if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
     if (d_max == d_min) return fail(AADFF_E_INVALID, "d_max == d_min");
     if (N == 0) return AADFF_OK;
     DeviceGuard guard(h->device);

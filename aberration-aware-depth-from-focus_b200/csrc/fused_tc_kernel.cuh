@@ -58,7 +58,7 @@ struct TcGroup {            // one accumulation group: one layer, or one <=256-c
     uint32_t w_off;         // byte offset of its first slab in the packed weights
     uint16_t K;             // 64 or 256
     uint16_t N;             // MMA N: multiple of 16, <= 256
-    uint16_t terms;         // 3 = hi*hi + lo*hi + hi*lo, 1 = hi*hi only
+    uint16_t terms;         // 3 = hi*hi + lo*hi + hi*lo, 2 = hi*hi + lo*hi (fp16 weights), 1 = hi*hi only
     uint16_t bias_off;      // float offset into the bias table
     uint16_t new_a;         // 1: consumes a freshly produced A operand (wait a_ready), 0: reuses it
     uint16_t tap0;          // head blocks: first tap (output feature) of the block
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             for (int gi = 0; gi < P.n_groups; ++gi) {
                 const uint32_t gN = P.g[gi].N;
                 const int nkc = P.g[gi].K / TC_SLAB_K;
-                const bool three = P.g[gi].terms == 3;
+                const bool three = P.g[gi].terms == 3;       // Ah*Wh + Al*Wh + Ah*Wl
+                const bool use_al = P.g[gi].terms >= 2;      // 2 terms: Ah*Wh + Al*Wh (weights rounded to fp16)
                 const bool new_a = P.g[gi].new_a != 0;
                 const uint32_t buf = gcount & 1;
                 if (gcount >= 2) {           // the epilogue must have drained group gcount-2
@@ -288,11 +289,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             umma_f16_ss(d_tmem, ah + 2 * KSTEP_A, db + STAGE_STEP, idesc, 1);
                             umma_f16_ss(d_tmem, ah + 3 * KSTEP_A, db + STAGE_STEP + kstep_b, idesc, 1);
                         }
-                        if (three) {
+                        if (use_al) {
                             umma_f16_ss(d_tmem, al, db, idesc, 1);
                             umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
-                            umma_commit(bar_empty(hi_stage));    // release the hi stage early: the 3-term ring is
-                        }                                        // only 64 KB deep and 4 MMAs cover the stall
+                            if (three) umma_commit(bar_empty(hi_stage));   // release the hi stage early: the 3-term
+                        }                                        // ring is only 64 KB deep, 4 MMAs cover the stall
                     }
                     __syncwarp();
                     if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     //      (fast mode only: in the 3-term modes the MMA warp runs ahead of the epilogue for the first
                     //      chunks, and waiting for the next A chunk here would hold back the stage release)
                     pre_waited = false;
-                    if (!three && it + 1 < nit) {
+                    if (!use_al && it + 1 < nit) {
                         tr.ev(0x500 + kc + kslab);
                         mbar_wait(bar_full(stage), fphase);
                         if (new_a) {
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             const float y = coord_y(min(h0 + ty, ra.H - 1), ra.H, ra.step_y);
             const float z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
             const float fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
-            const bool need_lo = P.g[0].terms == 3;
+            const bool need_lo = P.g[0].terms >= 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 // K-group (8 features) computed in this step: a contiguous quarter in fast mode, half of
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 afphase ^= 1u << buf;
                 tc_fence_after_sync();
                 tr.ev(0xB00 + gi);                           // accumulator gi complete
-                const bool need_lo = P.g[gi + 1].terms == 3;
+                const bool need_lo = P.g[gi + 1].terms >= 2;
                 const float* bias = s_bias + P.g[gi].bias_off;
                 const uint32_t t_acc = t_lane + buf * 256;
                 uint32_t rr[2][32], rf[2][16];

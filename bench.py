@@ -35,6 +35,7 @@ WORKLOADS = {  # name: (N, S, H, W, ks, description)
 CKPT = os.path.join(ROOT, "tests", "golden", "rf50mm_PSFNet480x640_ks11.pkl")
 DTYPES = {"parity": "f32 via fp16 hi/lo split (3 tcgen05 terms, f32 accumulate)",
           "mixed": "fp16 split for 3 layers then single fp16 term (f32 accumulate)",
+          "econ": "fp16 hi/lo split, 3 terms (L1-L4, head) / 2 terms (L5-L9), f32 accumulate",
           "fast": "f16 operands, f32 accumulate", "fp32": "f32"}
 
 
@@ -57,7 +58,8 @@ def executed_mma_flops_per_pixel(ks, mode):
     cores), head padded to a multiple of 16 columns, times the number of fp16 terms per layer."""
     head = (ks * ks + 15) // 16 * 16
     per_layer = [64 * 256] + [256 * 256] * 8 + [256 * head]
-    terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "fp32": [0] * 10}[mode]
+    terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "econ": [3] * 4 + [2] * 5 + [3],
+             "fp32": [0] * 10}[mode]
     return 2 * sum(t * m for t, m in zip(terms, per_layer))
 
 
@@ -260,7 +262,7 @@ def run_ours(args):
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for mode in [m for m in ("fast", "mixed") if m != args.mode]:
+        for mode in [m for m in ("econ", "fast", "mixed") if m != args.mode]:
             tt, _ = timed(mode, max(3, args.steps // 2), 2)
             extra[mode] = {"value": units / (statistics.mean(tt) * 1e-3) / 1e6, "unit": "Mpix*slices/s",
                            "dtype": DTYPES[mode]}
@@ -292,7 +294,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": int(units * (12 + 16 / S)),
                          "kernel": "fused_psfnet_render_kernel", "kernel_ms": ms_kernel,
                          "algorithmic_flops_per_pixel_slice": flops_per_pixel(ks),
-                         "executed_mma_terms": {"parity": 3, "fast": 1, "mixed": "3 for L1-L3, 1 after", "fp32": 0}[args.mode]},
+                         "executed_mma_terms": {"parity": 3, "fast": 1, "mixed": "3 for L1-L3, 1 after",
+                                                "econ": "3 for L1-L4 and head, 2 for L5-L9", "fp32": 0}[args.mode]},
             "checksum": float(checksum),
         }
         if extra:
@@ -313,7 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="parity", choices=["parity", "fast", "mixed", "fp32"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "econ", "fast", "mixed", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

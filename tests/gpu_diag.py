@@ -96,6 +96,7 @@ def stage_tc_parity_swap():
 def stage_tc_fast():
     _tc("fast")
     _tc("mixed")
+    _tc("econ")
 
 
 def stage_tc_ks31():
@@ -121,7 +122,7 @@ def stage_tc_ks31():
 def stage_speed():
     import torch
     from oracle import focal_stack_oracle as orc
-    for (N, S, H, W, ks, modes) in [(1, 5, 512, 512, 11, ("parity", "mixed", "fast", "fp32")),
+    for (N, S, H, W, ks, modes) in [(1, 5, 512, 512, 11, ("parity", "econ", "mixed", "fast", "fp32")),
                                     (16, 5, 256, 256, 11, ("parity", "fast")),
                                     (1, 2, 1080, 1920, 31, ("parity", "fast"))]:
         img, dm = orc.synthetic_rgbd(N, H, W, seed=1234)
