@@ -228,10 +228,12 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         if (rc) { aadff_psfnet_destroy(h); return rc; }
         rc = upload(w0b0, &h->d_w0b0);
         if (rc) { aadff_psfnet_destroy(h); return rc; }
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      h->smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      h->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     }
     *out = h;
     return AADFF_OK;
@@ -250,7 +252,8 @@ int aadff_psfnet_destroy(aadff_psfnet_t h) {
     return AADFF_OK;
 }
 
-static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st) {
+static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st, const float* probes = nullptr,
+                     float* psf_out = nullptr, long long n_probes = 0) {
     if (!h->tc_ok) return fail(AADFF_E_UNSUPPORTED, "tensor-core path unavailable: " + h->tc_why + " (use AADFF_MODE_FP32)");
     TcParams P{};
     P.ra = ra;
@@ -272,6 +275,12 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
     P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
     P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
+    if (probes != nullptr) {                                   // pred mode: 128 probes per tile, no image
+        P.probes = probes;
+        P.psf_out = psf_out;
+        P.n_probes = n_probes;
+        P.n_tiles = (n_probes + TC_M - 1) / TC_M;
+    }
     P.swap_lbo_sbo = (uint32_t)g_desc_swap.load();
     P.trace = g_trace.load();
     P.dbg = (uint32_t)g_dbg_flags.load();
@@ -295,10 +304,12 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st)
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;
     P.n_stages = (P.kslab == 2) ? 4 : stages;
     const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
-    if (P.trace != nullptr)
-        fused_psfnet_render_kernel<true><<<grid, TC_NT, smem, st>>>(P);
+    if (P.probes != nullptr)
+        fused_psfnet_render_kernel<false, true><<<grid, TC_NT, smem, st>>>(P);
+    else if (P.trace != nullptr)
+        fused_psfnet_render_kernel<true, false><<<grid, TC_NT, smem, st>>>(P);
     else
-        fused_psfnet_render_kernel<false><<<grid, TC_NT, smem, st>>>(P);
+        fused_psfnet_render_kernel<false, false><<<grid, TC_NT, smem, st>>>(P);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
@@ -388,6 +399,20 @@ int aadff_psfnet_pred_f32(aadff_psfnet_t h, const float* inp, float* psf, int64_
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
+}
+
+int aadff_psfnet_pred_tc_f32(aadff_psfnet_t h, const float* inp, float* psf, int64_t M, int mode, void* stream) {
+    if (!h || !inp || !psf) return fail(AADFF_E_INVALID, "null argument");
+    if (M < 0) return fail(AADFF_E_INVALID, "negative M");
+    if (mode == AADFF_MODE_FP32) return aadff_psfnet_pred_f32(h, inp, psf, M, stream);
+    if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
+    if (reinterpret_cast<uintptr_t>(inp) % 16) return fail(AADFF_E_INVALID, "inp must be 16-byte aligned");
+    if (M == 0) return AADFF_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    RenderArgs ra{};
+    ra.ks = h->ks; ra.N = 1; ra.S = 1; ra.H = 1; ra.W = 1; ra.C = 1; ra.Ctot = 1;
+    return launch_tc(h, ra, mode, static_cast<cudaStream_t>(stream), inp, psf, (long long)M);
 }
 
 int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, int N, int C, int H, int W, int ks,

@@ -79,6 +79,10 @@ struct TcParams {
     uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar;
     uint32_t swap_lbo_sbo;  // debug: descriptor field convention probe
     uint32_t dbg;           // what-if timing switches (results invalid): 1 = no weight copies, 2 = no A stores
+    // pred mode (kernel instantiated with PRED = true): probes [M,4] in, L1-normalised PSFs [M, ks*ks] out
+    const float* probes;
+    float* psf_out;
+    long long n_probes;
     unsigned long long* trace;  // optional [4 roles][TC_TRACE_N] event log of CTA 0 (nullptr = off)
 };
 
@@ -153,7 +157,7 @@ __device__ __forceinline__ void epi_group8(const uint32_t* acc, const float* bia
 constexpr int TC_WARP_PRODUCER = TC_EPI_WARPS;       // warp 8
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;        // warp 9
 
-template <bool TRACE>
+template <bool TRACE, bool PRED>
 __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -365,13 +369,20 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             h0 = (txy / P.tiles_x) * TC_TILE_H;
             w0 = (txy % P.tiles_x) * TC_TILE_W;
         };
+        float4 nx_in = make_float4(0.f, 0.f, 0.f, 0.f);   // pred mode: the probe (x, y, z, foc_z) of this row
         auto fetch_dz = [&](long long tile, float& d, float& f) {
             if (tile < P.n_tiles) {
-                int n, s, h0, w0;
-                tile_coords(tile, n, s, h0, w0);
-                const int hc = min(h0 + ty, ra.H - 1), wc = min(w0 + tx, ra.W - 1);
-                d = __ldg(ra.depth + ((long long)n * ra.H + hc) * ra.W + wc);
-                f = __ldg(ra.foc + (long long)n * ra.S + s);
+                if constexpr (PRED) {
+                    const long long m = tile * TC_M + row;
+                    nx_in = (m < P.n_probes) ? __ldg(reinterpret_cast<const float4*>(P.probes) + m)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    int n, s, h0, w0;
+                    tile_coords(tile, n, s, h0, w0);
+                    const int hc = min(h0 + ty, ra.H - 1), wc = min(w0 + tx, ra.W - 1);
+                    d = __ldg(ra.depth + ((long long)n * ra.H + hc) * ra.W + wc);
+                    f = __ldg(ra.foc + (long long)n * ra.S + s);
+                }
             }
         };
         float nx_depth = 0.f, nx_foc = 0.f;
@@ -381,12 +392,17 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         //      Runs one tile AHEAD: right after the previous tile's last head block has retired (the A buffer is
         //      free again) and BEFORE that tile's gather, so the L1 MMAs of tile t overlap the gather of tile t-1.
         auto layer0 = [&](long long t) {
-            int n, s, h0, w0;
-            tile_coords(t, n, s, h0, w0);
-            const float x = coord_x(min(w0 + tx, ra.W - 1), ra.W, ra.step_x);
-            const float y = coord_y(min(h0 + ty, ra.H - 1), ra.H, ra.step_y);
-            const float z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
-            const float fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
+            float x, y, z, fz;
+            if constexpr (PRED) {
+                x = nx_in.x; y = nx_in.y; z = nx_in.z; fz = nx_in.w;
+            } else {
+                int n, s, h0, w0;
+                tile_coords(t, n, s, h0, w0);
+                x = coord_x(min(w0 + tx, ra.W - 1), ra.W, ra.step_x);
+                y = coord_y(min(h0 + ty, ra.H - 1), ra.H, ra.step_y);
+                z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
+                fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
+            }
             const bool need_lo = P.g[0].terms >= 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -415,10 +431,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         if ((long long)blockIdx.x < P.n_tiles) layer0(blockIdx.x);
 
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            int n, s, h0, w0;
-            tile_coords(tile, n, s, h0, w0);
+            int n = 0, s = 0, h0 = 0, w0 = 0;
+            if constexpr (!PRED) tile_coords(tile, n, s, h0, w0);
             const int h = h0 + ty, w = w0 + tx;
-            const bool valid = (h < ra.H) && (w < ra.W);
+            const long long m_row = tile * TC_M + row;      // pred mode: probe index of this thread's row
+            const bool valid = PRED ? (m_row < P.n_probes) : ((h < ra.H) && (w < ra.W));
             tr.ev(0x800);                                // tile start (its layer 0 is already done)
             fetch_dz(tile + gridDim.x, nx_depth, nx_foc);    // depth / focus of the next tile, used by layer0 below
 
@@ -429,7 +446,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             const float* img_n = ra.img + ((long long)n * ra.Ctot + ra.c0) * ra.H * ra.W;
             const long long cstride = (long long)ra.H * ra.W;
             auto halo_fetch = [&](int idx, float4& v) -> int {       // returns the smem slot or -1
-                if (idx >= HH * HW) return -1;
+                if (PRED || idx >= HH * HW) return -1;
                 const int yy = idx / HW, xx = idx - yy * HW;
                 const int gy = min(max(h0 + yy - r, 0), ra.H - 1), gx = min(max(w0 + xx - r, 0), ra.W - 1);
                 const float* px = img_n + (long long)gy * ra.W + gx;
@@ -493,7 +510,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 if (hslot >= 0) s_halo[hslot] = hv;
                 ++gcount;
             }
-            for (int idx = P.n_hidden * TC_EPI_THREADS + et; idx < HH * HW; idx += TC_EPI_THREADS) {   // remainder
+            for (int idx = P.n_hidden * TC_EPI_THREADS + et; !PRED && idx < HH * HW; idx += TC_EPI_THREADS) {   // remainder
                 float4 hv;
                 const int hslot = halo_fetch(idx, hv);
                 s_halo[hslot] = hv;
@@ -526,7 +543,18 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     int off = i * TC_HALO_PITCH + j;
                     const int nvalid = kk - tap_first;     // >= 32 for every group but the padded last one
                     tmem_ld_wait();
-                    if (nvalid >= 32) {
+                    if constexpr (PRED) {
+                        // un-normalised sigmoid values go straight to the output; they are rescaled below
+                        float* orow = P.psf_out + m_row * kk + tap_first;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            if (u < nvalid) {
+                                const float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
+                                ssum += sg;
+                                if (valid) orow[u] = sg;
+                            }
+                        }
+                    } else if (nvalid >= 32) {
                         // branch-free so that the MUFU / LDS latencies of different taps overlap
 #pragma unroll
                         for (int u = 0; u < 32; ++u) {
@@ -561,6 +589,22 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_accfree(buf));
                 ++gcount;
+            }
+            if constexpr (PRED) {
+                // ---- exchange the partial sums of the two column halves, then rescale what this thread wrote
+                s_red[row * 5 + hh] = ssum;
+                named_bar_sync(2 + q, 64);
+                const float inv = 1.0f / fmaxf(s_red[row * 5] + s_red[row * 5 + 1], 1e-12f);
+                if (valid) {
+                    for (int gi = P.n_hidden; gi < P.n_groups; ++gi) {
+                        for (int c32 = hh * 32; c32 < P.g[gi].N; c32 += 64) {
+                            const int t0 = P.g[gi].tap0 + c32;
+                            float* orow = P.psf_out + m_row * kk + t0;
+                            for (int u = 0; u < 32 && t0 + u < kk; ++u) orow[u] *= inv;
+                        }
+                    }
+                }
+                continue;
             }
             // ---- combine the two column-halves of each pixel, normalise (F.normalize p=1), store
             if (hh == 1) {

@@ -73,6 +73,9 @@ int aadff_render_stack_host_f32(aadff_psfnet_t net, const float* img, const floa
 /* Replaces PSFNet.pred (deeplens/psfnet.py:375-390) for arbitrary probes:
  *   inp [M,4] (x, y, z, foc_z) -> psf [M, ks*ks], L1-normalised; fp32 arithmetic; device ptrs. */
 int aadff_psfnet_pred_f32(aadff_psfnet_t net, const float* inp, float* psf, int64_t M, void* stream);
+/* The same on the tensor-core path (the fused kernel with the gather replaced by a PSF store); `mode` as for
+ * aadff_render_stack_f32 (AADFF_MODE_FP32 forwards to the call above).  inp must be 16-byte aligned.          */
+int aadff_psfnet_pred_tc_f32(aadff_psfnet_t net, const float* inp, float* psf, int64_t M, int mode, void* stream);
 
 /* Replaces local_psf_render (deeplens/render_psf.py:76-107) for a PSF tensor in memory:
  *   img [N,C,H,W], psf [N,H,W,ks,ks] -> out [N,C,H,W]; device pointers.                        */

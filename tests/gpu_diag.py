@@ -223,6 +223,9 @@ def stage_rows():
     inp = torch.rand(1 << 20, 4, device="cuda")
     ms = timeit(lambda: lens.pred(inp), iters=3)
     print(f"pred M=1Mi k11 (fp32 kernel): {ms:.3f} ms  {inp.shape[0] / ms / 1e3:.1f} Mprobes/s", flush=True)
+    for mode in ("parity", "fast"):
+        ms = timeit(lambda: lens.pred(inp, mode=mode), iters=5)
+        print(f"pred M=1Mi k11 (tensor-core, {mode}): {ms:.3f} ms  {inp.shape[0] / ms / 1e3:.1f} Mprobes/s", flush=True)
 
 
 STAGES = {k[6:]: v for k, v in list(globals().items()) if k.startswith("stage_")}

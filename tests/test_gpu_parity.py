@@ -91,6 +91,13 @@ def test_pred_golden(lens):
     assert psf.shape == (64, 11, 11)
     assert maxabs(psf, T(g["psf"])) < 1e-6
     assert abs(float(psf[1, 5, 5]) - 0.810939252) < 1e-6          # SURVEY.md 8c literal
+    for mode, tol in (("parity", 1e-5), ("econ", 1e-4), ("fast", 5e-2)):   # tensor-core pred (PSF values, not images)
+        tc = lens.pred(T(g["inp"]).cuda(), mode=mode)
+        assert tc.shape == (64, 11, 11) and maxabs(tc, T(g["psf"])) < tol, mode
+        assert float((tc.sum((-1, -2)) - 1).abs().max()) < 1e-5
+    big = torch.rand(1000, 4, generator=torch.Generator().manual_seed(3))
+    big[:, :2] = big[:, :2] * 2 - 1
+    assert maxabs(lens.pred(big.cuda(), mode="parity"), lens.pred(big.cuda())) < 1e-5      # ragged M (not % 128)
     grid = lens.pred(T(g["inp"]).cuda().reshape(8, 8, 4))           # [H,W,4] -> [H,W,ks,ks]
     assert grid.shape == (8, 8, 11, 11) and maxabs(grid.reshape(64, 11, 11), psf) == 0.0
 
