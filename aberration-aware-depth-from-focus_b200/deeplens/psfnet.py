@@ -174,6 +174,17 @@ class PSFNet(nn.Module):
         self._launch(img, depth, foc, out, strides, mode)
         return out
 
+    @torch.no_grad()
+    def simulate_focal_stack(self, aif, depth_m, n_stack, layout="BCSHW", mode=None):
+        """The focal-stack simulation block of the training scripts (2_aber_aware_dff_aif.py:101-114) in one
+        call with no host synchronisation: focus distances from `select_focus_dist(depth_m, n_stack, 'linear')`
+        (metres, device-side reductions), then ONE fused launch for all slices.
+        aif [B,C,H,W] in [0,1], depth_m [B,1,H,W] metres (0 = invalid) -> (stack [B,C,S,H,W], focus_dists [B,S] m)."""
+        from dff.utils import select_focus_dist
+        focus_dists = select_focus_dist(depth_m, n_stack, mode='linear')
+        stack = self.render_stack(aif, -depth_m * 1e3, -focus_dists * 1e3, layout=layout, mode=mode)
+        return stack, focus_dists
+
     # ------------------------------------------------------------------ utils
     def depth2z(self, depth):
         z = (depth - self.d_min) / (self.d_max - self.d_min)

@@ -323,3 +323,39 @@ def test_multi_gpu_sharded_render_matches_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29613",
                           os.path.join(root, "tests", "gpu_multi_verify.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MULTI_GPU_VERIFY PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_simulate_focal_stack_matches_training_loop(lens):
+    """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
+    from dff.utils import select_focus_dist
+    img, dm = orc.synthetic_rgbd(2, 64, 96, seed=11)
+    img, dm = img.cuda(), dm.cuda()
+    stack, foc = lens.simulate_focal_stack(img, dm, 5)
+    ref_foc = select_focus_dist(dm, 5, mode='linear')
+    loop = torch.stack([lens.render(img, depth=-dm * 1e3, foc_dist=-ref_foc[:, i] * 1e3) for i in range(5)], dim=2)
+    assert torch.equal(foc, ref_foc) and torch.equal(stack, loop)
+
+
+def test_render_is_cuda_graph_capturable(lens):
+    """The C-ABI render never allocates or synchronises: it can be captured in a CUDA graph and replayed."""
+    img, dm = orc.synthetic_rgbd(1, 64, 64, seed=21)
+    foc = -orc.synthetic_focus(dm, 4).cuda() * 1e3
+    img, dep = img.cuda(), -dm.cuda() * 1e3
+    eager = lens.render_stack(img, dep, foc)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        lens.render_stack(img, dep, foc)                  # warm-up on the capture stream
+        with torch.cuda.graph(graph, stream=side):
+            captured = lens.render_stack(img, dep, foc)
+    torch.cuda.current_stream().wait_stream(side)
+    captured.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    img.mul_(0.5)                                         # new data in the same buffers, replay again
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, lens.render_stack(img, dep, foc))
