@@ -94,7 +94,8 @@ struct aadff_psfnet {
     TcGroup groups[TC_MAX_GROUPS]{};
     int n_groups = 0, n_hidden = 0, n_bias = 0;
     // host-call workspace
-    cudaStream_t ws_stream = nullptr;
+    cudaStream_t ws_stream = nullptr, ws_copy_stream = nullptr;
+    std::vector<cudaEvent_t> ws_events;
     float* ws = nullptr;
     size_t ws_bytes = 0;
 };
@@ -248,6 +249,8 @@ int aadff_psfnet_destroy(aadff_psfnet_t h) {
     cudaFree(h->d_w0b0);
     cudaFree(h->ws);
     if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
+    if (h->ws_copy_stream) cudaStreamDestroy(h->ws_copy_stream);
+    for (cudaEvent_t e : h->ws_events) cudaEventDestroy(e);
     delete h;
     return AADFF_OK;
 }
@@ -315,9 +318,19 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     return AADFF_OK;
 }
 
+static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, int foc_stride,
+                             float* out, const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                             float d_max, int mode, void* stream);
+
 int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, float* out,
                            const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
                            float d_max, int mode, void* stream) {
+    return render_stack_impl(h, img, depth, foc, S, out, out_strides, N, C, S, H, W, d_min, d_max, mode, stream);
+}
+
+static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, int foc_stride,
+                             float* out, const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                             float d_max, int mode, void* stream) {
     if (!h || !img || !depth || !foc || !out || !out_strides) return fail(AADFF_E_INVALID, "null argument");
     if (N < 0 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
     if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
@@ -331,6 +344,7 @@ int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* dept
     ra.os_n = out_strides[0]; ra.os_c = out_strides[1]; ra.os_s = out_strides[2];
     ra.os_h = out_strides[3]; ra.os_w = out_strides[4];
     ra.N = N; ra.S = S; ra.H = H; ra.W = W; ra.ks = h->ks; ra.Ctot = C;
+    ra.foc_stride = foc_stride;
     ra.d_min = d_min;
     ra.d_range = d_max - d_min;
     ra.step_x = (W > 1) ? (1.0f - (-1.0f)) / (float)(W - 1) : 0.f;
@@ -379,9 +393,29 @@ int aadff_render_stack_host_f32(aadff_psfnet_t h, const float* img, const float*
     CUDA_TRY(cudaMemcpyAsync(d_dep, depth, n_dep * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_foc, foc, n_foc * sizeof(float), cudaMemcpyHostToDevice, st));
     const int64_t strides[5] = {(int64_t)C * S * H * W, (int64_t)S * H * W, (int64_t)H * W, W, 1};
-    int rc = aadff_render_stack_f32(h, d_img, d_dep, d_foc, d_out, strides, N, C, S, H, W, d_min, d_max, mode, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // One launch per focal slice; the device->host copy of slice s runs on a second stream while the kernel of
+    // slice s+1 computes, so only the last slice's copy is exposed.  (A slice is C planes of H*W floats, S*H*W
+    // apart, per image: one 2-D copy per image.)
+    if (!h->ws_copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->ws_copy_stream, cudaStreamNonBlocking));
+    if (h->ws_events.size() < (size_t)S) {
+        const size_t old = h->ws_events.size();
+        h->ws_events.resize(S);
+        for (size_t i = old; i < (size_t)S; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->ws_events[i], cudaEventDisableTiming));
+    }
+    const size_t plane = (size_t)H * W * sizeof(float);
+    for (int s = 0; s < S; ++s) {
+        int rc = render_stack_impl(h, d_img, d_dep, d_foc + s, S, d_out + (size_t)s * H * W, strides, N, C, 1, H, W, d_min,
+                                   d_max, mode, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ws_events[s], st));
+        CUDA_TRY(cudaStreamWaitEvent(h->ws_copy_stream, h->ws_events[s], 0));
+        for (int n = 0; n < N; ++n) {
+            const size_t off = ((size_t)n * C * S + s) * H * W;
+            CUDA_TRY(cudaMemcpy2DAsync(out + off, (size_t)S * plane, d_out + off, (size_t)S * plane, plane, C,
+                                       cudaMemcpyDeviceToHost, h->ws_copy_stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->ws_copy_stream));
     CUDA_TRY(cudaStreamSynchronize(st));
     return AADFF_OK;
 }

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     tile_coords(tile, n, s, h0, w0);
                     const int hc = min(h0 + ty, ra.H - 1), wc = min(w0 + tx, ra.W - 1);
                     d = __ldg(ra.depth + ((long long)n * ra.H + hc) * ra.W + wc);
-                    f = __ldg(ra.foc + (long long)n * ra.S + s);
+                    f = __ldg(ra.foc + (long long)n * ra.foc_stride + s);
                 }
             }
         };

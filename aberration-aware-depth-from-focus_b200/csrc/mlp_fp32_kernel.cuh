@@ -79,7 +79,7 @@ mlp_fp32_kernel(Fp32Net net, RenderArgs ra, const float* __restrict__ probes, fl
                     o[0] = coord_x(w, ra.W, ra.step_x);
                     o[1] = coord_y(h, ra.H, ra.step_y);
                     o[2] = depth_to_z(__ldg(ra.depth + ((long long)n * ra.H + h) * ra.W + w), ra.d_min, ra.d_range);
-                    o[3] = depth_to_z(__ldg(ra.foc + (long long)n * ra.S + s), ra.d_min, ra.d_range);
+                    o[3] = depth_to_z(__ldg(ra.foc + (long long)n * ra.foc_stride + s), ra.d_min, ra.d_range);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) o[c] = __ldg(probes + id * 4 + c);

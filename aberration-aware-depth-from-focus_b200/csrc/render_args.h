@@ -10,11 +10,12 @@ constexpr int MAX_LAYERS = 16;
 struct RenderArgs {
     const float* img;     // [N,C,H,W] fp32, contiguous
     const float* depth;   // [N,H,W]   fp32, mm (<= 0)
-    const float* foc;     // [N,S]     fp32, mm (< 0)
+    const float* foc;     // [N,S]     fp32, mm (< 0); row stride foc_stride (a slice window of a wider array)
     float* out;           // element strides below
     long long os_n, os_c, os_s, os_h, os_w;
     int N, C, S, H, W, ks;  // C = channels rendered by this launch (<= 4)
     int Ctot, c0;           // img/out have Ctot channels; this launch covers [c0, c0+C)
+    int foc_stride;         // elements between consecutive images in foc (>= S)
     float d_min, d_range; // d_min = -200, d_range = d_max - d_min = -19800
     float step_x, step_y; // torch.linspace steps: 2/(W-1), -2/(H-1)
 };
