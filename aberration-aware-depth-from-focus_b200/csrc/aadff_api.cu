@@ -284,7 +284,6 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
         P.n_probes = n_probes;
         P.n_tiles = (n_probes + TC_M - 1) / TC_M;
     }
-    P.swap_lbo_sbo = (uint32_t)g_desc_swap.load();
     P.trace = g_trace.load();
     P.dbg = (uint32_t)g_dbg_flags.load();
     // shared-memory carve-up

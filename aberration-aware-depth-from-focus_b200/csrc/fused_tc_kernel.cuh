@@ -9,14 +9,15 @@
 // Work unit: a tile of 8 x 16 = 128 output pixels of one (image, slice); MMA M = 128, one
 // TMEM lane per pixel.  A persistent CTA (one per SM) walks tiles round-robin.
 //
-//   warp 0      weight producer: streams pre-packed fp16 weight slabs L2 -> smem ring
-//               (cp.async.bulk + mbarrier complete_tx), also owns TMEM alloc/dealloc
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::f16, M128 x N<=256 x K16),
-//               accumulators ping-pong between TMEM columns [0,256) and [256,512)
-//   warps 2-9   epilogue/compute (256 threads, two warps per TMEM lane quadrant):
+//   warps 0-7   epilogue/compute (256 threads, two warps per TMEM lane quadrant):
 //               layer 0 (4->64) in fp32 FFMA, per-layer epilogue (TMEM -> +bias -> ReLU ->
 //               fp16 hi/lo split -> K-major smem operand for the next layer), and the head
 //               epilogue (sigmoid -> k x k gather from the smem halo tile -> normalise -> store)
+//   warp 8      weight producer: streams pre-packed fp16 weight slabs L2 -> smem ring
+//               (cp.async.bulk + mbarrier complete_tx), also owns TMEM alloc/dealloc
+//   warp 9      MMA issuer: converged warp, an elected lane issues tcgen05.mma (kind::f16,
+//               M128 x N<=256 x K16); accumulators ping-pong between TMEM columns [0,256), [256,512)
+//   (the two single-thread roles are the highest warp ids on purpose, see TC_WARP_PRODUCER)
 //
 // Precision: fp16 operands cannot hold the activations/weights to the 1e-4 image tolerance
 // (SURVEY.md 7.3), so in parity mode every product is evaluated as
@@ -24,7 +25,7 @@
 // with fp32 accumulation in TMEM: three tcgen05.mma per K-step.  "terms" is per layer, so
 // fast (1-term) and mixed modes are the same kernel.
 //
-// Intra-tile pipelining: the epilogue of layer l hands its output to the MMA warp in 64-column
+// Intra-tile pipelining: the epilogue of layer l hands its output to the MMA warp in 32/64-column
 // chunks (a_ready[j]); the MMAs of layer l+1 for K-chunk j start as soon as chunk j is in smem and
 // write the *other* accumulator, so the tensor pipe idles only for the first chunk of each epilogue.
 #pragma once
@@ -77,7 +78,6 @@ struct TcParams {
     long long n_tiles;
     // shared-memory byte offsets
     uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar;
-    uint32_t swap_lbo_sbo;  // debug: descriptor field convention probe
     uint32_t dbg;           // what-if timing switches (results invalid): 1 = no weight copies, 2 = no A stores
     // pred mode (kernel instantiated with PRED = true): probes [M,4] in, L1-normalised PSFs [M, ks*ks] out
     const float* probes;

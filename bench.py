@@ -31,6 +31,10 @@ WORKLOADS = {  # name: (N, S, H, W, ks, description)
     "c2": (1, 5, 512, 512, 11, "AiFNet config: 5-slice focal stack at 512x512, rf50mm ckpt, k=11"),
     "c3": (16, 5, 256, 256, 11, "DFVNet config: batch 16 x 5 slices at 256x256, rf50mm ckpt, k=11"),
     "c4": (1, 10, 1080, 1920, 31, "large render: 10 slices at 1920x1080, k=31, seeded random PSFNet"),
+    # BASELINE configs[4] (AiF training step, batch sweep): only its focal-stack simulation half is on the path;
+    # AiFNet itself is a downstream consumer (out of scope), so these time the simulation of one training batch
+    "c5b8": (8, 5, 512, 512, 11, "AiF training batch: 8 x 5 slices at 512x512 (simulation half of the step), k=11"),
+    "c5b64": (64, 5, 512, 512, 11, "AiF training batch: 64 x 5 slices at 512x512 (simulation half of the step), k=11"),
 }
 CKPT = os.path.join(ROOT, "tests", "golden", "rf50mm_PSFNet480x640_ks11.pkl")
 DTYPES = {"parity": "f32 via fp16 hi/lo split (3 tcgen05 terms, f32 accumulate)",

@@ -234,7 +234,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--run":
         STAGES[sys.argv[2]]()
         sys.exit(0)
-    names = sys.argv[1:] or ["umma", "fp32", "tc_parity", "tc_parity_swap", "tc_fast", "tc_ks31", "speed"]
+    names = sys.argv[1:] or ["umma", "fp32", "tc_parity", "tc_fast", "tc_ks31", "speed", "rows", "mma_timing"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a")
     for name in names:
