@@ -15,6 +15,7 @@
 #include "gather_kernel.cuh"
 #include "mlp_fp32_kernel.cuh"
 #include "thinlens_kernel.cuh"
+#include "focus_kernel.cuh"
 
 using namespace aadff;
 
@@ -532,6 +533,17 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
+    return AADFF_OK;
+}
+
+int aadff_select_focus_f32(const float* depth_m, int B, int64_t HW, int num, float* out, void* stream) {
+    if (!depth_m || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || HW < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (num <= 3) return fail(AADFF_E_INVALID, "Focal stack size is too small");   // the reference asserts num > 3
+    if (B == 0) return AADFF_OK;
+    select_focus_kernel<<<B, FOCUS_NT, 0, static_cast<cudaStream_t>(stream)>>>(depth_m, (long long)HW, num, out);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
 }
 

@@ -91,6 +91,12 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
                               int W, int ks, float foc_len, float fnum, float pixel_size, float d_lo, float d_hi,
                               int flip_sign, void* stream);
 
+/* Replaces select_focus_dist(depth, num, mode='linear') (dff/utils.py:4-51), the producer of foc_dist in the
+ * training loop: per image the minimum over valid (> 0) depths and the maximum depth, then `num` (> 3) focus
+ * distances linearly between them, ascending.  depth_m [B, HW] (metres, any unit really), out [B, num]; device.
+ * An image without a single valid depth yields +inf (the reference raises on it).                          */
+int aadff_select_focus_f32(const float* depth_m, int B, int64_t HW, int num, float* out, void* stream);
+
 /* Number of kernels launched by this library in the calling process (bench bookkeeping).      */
 int64_t aadff_launch_count(void);
 
