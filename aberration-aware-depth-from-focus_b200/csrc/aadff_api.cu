@@ -460,25 +460,39 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kk = ks * ks;
-    int P = 32, nbuf = 1;
+    int P = 32;
     while (P > 4 && P * kk * 4 > GS_BUF_BYTES) P >>= 1;
-    // (two half-size chunks per warp -- nbuf = 2 -- measured slower: 16-pixel chunks leave the one-lane-per-pixel
-    //  fast path; the kernel keeps the option, the host does not use it)
     const bool stream_ok = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(psf) % 16 == 0) && (P * kk * 4 <= GS_BUF_BYTES);
     if (stream_ok) {
-        // HBM-streaming path: cp.async.bulk PSF chunks, smem halo tile
-        const int HH = GS_TILE_H + ks - 1, pitch = (GS_TILE_W + ks - 1) | 1;
-        const int smem = GS_TILE_H * GS_BUF_BYTES + GS_MAXC * HH * pitch * 4 + 16 * GS_TILE_H;
-        static std::atomic<int> attr_smem{0};
-        if (attr_smem.load() < smem) {
-            CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_smem.store(smem);
+        // HBM-streaming path: cp.async.bulk PSF chunks, smem halo tile.  One 16 KB chunk buffer per warp, 8 warps.
+        // (Two buffers per warp only fit with 6 warps and measured 20 % slower: the kernel is limited by the
+        //  arithmetic/latency of its 8 warps, not by exposed copy latency -- debug flag 64 selects that variant.)
+        const int nbuf = (P == 32 && g_dbg_flags.load() == 64) ? 2 : 1;
+        const int nw = (nbuf == 2) ? GS_TILE_H_2BUF : GS_TILE_H_1BUF;
+        const int buf_bytes = (P * kk * 4 + 127) / 128 * 128;
+        const int HH = nw + ks - 1, pitch = (GS_TILE_W + ks - 1) | 1;
+        const int smem = nw * nbuf * buf_bytes + GS_MAXC * HH * pitch * 4 + 16 * nw;
+        static std::atomic<int> attr_smem8{0}, attr_smem6{0};
+        std::atomic<int>& attr = (nw == GS_TILE_H_1BUF) ? attr_smem8 : attr_smem6;
+        if (attr.load() < smem) {
+            if (nw == GS_TILE_H_1BUF)
+                CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel<GS_TILE_H_1BUF>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            else
+                CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel<GS_TILE_H_2BUF>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr.store(smem);
         }
-        const long long tiles = (long long)N * ((H + GS_TILE_H - 1) / GS_TILE_H) * ((W + GS_TILE_W - 1) / GS_TILE_W);
+        const long long tiles = (long long)N * ((H + nw - 1) / nw) * ((W + GS_TILE_W - 1) / GS_TILE_W);
         const int grid = (int)std::min<long long>(tiles, sms);
         for (int c0 = 0; c0 < C; c0 += GS_MAXC) {
-            local_psf_stream_kernel<<<grid, GS_TILE_H * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0,
-                                                                        std::min(GS_MAXC, C - c0), P, nbuf);
+            const int cn = std::min(GS_MAXC, C - c0);
+            if (nw == GS_TILE_H_1BUF)
+                local_psf_stream_kernel<GS_TILE_H_1BUF><<<grid, nw * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0, cn,
+                                                                                   P, nbuf, buf_bytes);
+            else
+                local_psf_stream_kernel<GS_TILE_H_2BUF><<<grid, nw * 32, smem, st>>>(img, psf, out, N, C, H, W, ks, c0, cn,
+                                                                                   P, nbuf, buf_bytes);
             g_launches.fetch_add(1);
             CUDA_TRY(cudaGetLastError());
         }

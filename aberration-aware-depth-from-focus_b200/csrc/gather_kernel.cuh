@@ -19,24 +19,27 @@
 
 namespace aadff {
 
-constexpr int GS_TILE_H = 8;                    // = warps per CTA
+constexpr int GS_TILE_H_1BUF = 8;               // warps per CTA (= tile rows), one 16 KB chunk buffer per warp
+constexpr int GS_TILE_H_2BUF = 6;               // warps per CTA with two chunk buffers per warp
 constexpr int GS_TILE_W = 32;
 constexpr int GS_BUF_BYTES = 16384;             // per-warp PSF chunk buffer
 constexpr int GS_MAXC = 4;
 
-__global__ void __launch_bounds__(GS_TILE_H * 32, 1)
+template <int NW>      // warps per CTA = tile rows
+__global__ void __launch_bounds__(NW * 32, 1)
 local_psf_stream_kernel(const float* __restrict__ img, const float* __restrict__ psf, float* __restrict__ out,
                         int N, int C, int H, int W, int ks, int c0, int cn, int P /*pixels per chunk*/,
-                        int nbuf /*1 or 2 chunk buffers per warp*/) {
+                        int nbuf /*1 or 2 chunk buffers per warp*/, int buf_bytes /*per chunk buffer*/) {
+    constexpr int GS_TILE_H = NW;
     extern __shared__ __align__(128) uint8_t gsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kk = ks * ks, r = (ks - 1) / 2;
     const int HH = GS_TILE_H + ks - 1, HW = GS_TILE_W + ks - 1;
     const int pitch = HW | 1;                                  // odd pitch: row-to-row bank skew
-    const int buf_floats = GS_BUF_BYTES / 4 / nbuf;
-    float* s_psf = reinterpret_cast<float*>(gsm) + warp * (GS_BUF_BYTES / 4);
-    float* s_img = reinterpret_cast<float*>(gsm + GS_TILE_H * GS_BUF_BYTES);    // [cn][HH][pitch]
-    const uint32_t bar = smem_u32(gsm + GS_TILE_H * GS_BUF_BYTES + (size_t)GS_MAXC * HH * pitch * 4) + 16u * warp;
+    const int buf_floats = buf_bytes / 4;
+    float* s_psf = reinterpret_cast<float*>(gsm) + warp * nbuf * buf_floats;
+    float* s_img = reinterpret_cast<float*>(gsm + (size_t)GS_TILE_H * nbuf * buf_bytes);    // [cn][HH][pitch]
+    const uint32_t bar = smem_u32(gsm + (size_t)GS_TILE_H * nbuf * buf_bytes + (size_t)GS_MAXC * HH * pitch * 4) + 16u * warp;
     if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); }
     fence_mbar_init();
     __syncthreads();

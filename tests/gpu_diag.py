@@ -204,13 +204,17 @@ def stage_rows():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
-    for (N, H, W, ks) in [(1, 480, 640, 11), (4, 512, 512, 11), (1, 540, 960, 31)]:
+    for (N, H, W, ks) in [(1, 480, 640, 11), (4, 512, 512, 11), (16, 512, 512, 11), (4, 512, 512, 7), (1, 540, 960, 31)]:
         img = torch.rand(N, 3, H, W, device="cuda")
         psf = torch.rand(N, H, W, ks, ks, device="cuda")
-        ms = timeit(lambda: aadff_b200.local_psf_render(img, psf, ks))
-        px = N * H * W
-        gb = px * (ks * ks * 4 + 24) / 1e9
-        print(f"gather N{N} {H}x{W} k{ks}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  {gb / ms * 1e3:.0f} GB/s", flush=True)
+        for flags in (0,):             # 64 = two chunk buffers per warp with 6 warps (measured slower)
+            aadff_b200.native.lib.aadff_debug_set_flags(flags)
+            ms = timeit(lambda: aadff_b200.local_psf_render(img, psf, ks))
+            px = N * H * W
+            gb = px * (ks * ks * 4 + 24) / 1e9
+            print(f"gather N{N} {H}x{W} k{ks} flags={flags}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  {gb / ms * 1e3:.0f} GB/s",
+                  flush=True)
+        aadff_b200.native.lib.aadff_debug_set_flags(0)
     from deeplens.psfnet import ThinLens
     for (N, H, W, ks) in [(4, 512, 512, 11), (1, 1080, 1920, 31)]:
         tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=ks, sensor_size=[36.0, 24.0], sensor_res=(H, W)).to("cuda")
