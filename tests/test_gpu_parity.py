@@ -361,3 +361,27 @@ def test_render_is_cuda_graph_capturable(lens):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(captured, lens.render_stack(img, dep, foc))
+
+
+@pytest.mark.parametrize("ks", [1, 3, 5, 7, 9, 13, 21, 27])
+def test_other_kernel_sizes_vs_oracle(pkg, ks):
+    """Kernel sizes without a shipped checkpoint: seeded PSFNet weights (+ random biases) in the fused kernel
+    (head padded to a multiple of 16 columns, 1..3 head blocks) against the CPU oracle."""
+    Ws, bs = orc.seeded_psfnet_weights(ks, seed=ks)
+    gen = torch.Generator().manual_seed(100 + ks)
+    bs = [(torch.rand(b.shape, generator=gen) - 0.5) * 0.2 for b in bs]
+    l = pkg.PSFNet(kernel_size=ks, device="cuda")
+    sd = {}
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        sd[f"net.{2 * i}.weight"], sd[f"net.{2 * i}.bias"] = W, b
+    l.psfnet.load_state_dict(sd)
+    img, dm = orc.synthetic_rgbd(2, 24, 40, seed=ks)
+    foc = -orc.synthetic_focus(dm, 2) * 1e3
+    ref = orc.render_stack(Ws, bs, img, -dm * 1e3, foc, ks)
+    for mode in ("parity", "fp32", "fast"):
+        out = l.render_stack(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode=mode)
+        assert maxabs(out, ref) < TOL[mode], (ks, mode)
+    probes = torch.rand(300, 4, generator=gen)
+    ref_psf = orc.mlp_forward(Ws, bs, probes).reshape(-1, ks, ks)
+    assert maxabs(l.pred(probes.cuda()), ref_psf) < 2e-6
+    assert maxabs(l.pred(probes.cuda(), mode="parity"), ref_psf) < 1e-5
