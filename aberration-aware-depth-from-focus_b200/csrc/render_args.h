@@ -22,10 +22,12 @@ struct RenderArgs {
 
 // torch.linspace(-1, 1, W)[w]: fma(step, w, start) in the first half, fma(-step, W-1-w, end) after
 __host__ __device__ __forceinline__ float coord_x(int w, int W, float step) {
+    if (W == 1) return -1.0f;                                   // linspace(a, b, 1) = [a]
     return (w < W / 2) ? fmaf(step, (float)w, -1.0f) : fmaf(-step, (float)(W - 1 - w), 1.0f);
 }
 // torch.linspace(1, -1, H)[h]
 __host__ __device__ __forceinline__ float coord_y(int h, int H, float step) {
+    if (H == 1) return 1.0f;
     return (h < H / 2) ? fmaf(step, (float)h, 1.0f) : fmaf(-step, (float)(H - 1 - h), -1.0f);
 }
 // PSFNet.depth2z (deeplens/psfnet.py:447-450): clamp((d - d_min) / (d_max - d_min), 0, 1), IEEE division

@@ -203,7 +203,8 @@ def test_thinlens_and_focus_golden(pkg):
 
 
 # --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
-@pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17), (2, 3, 7, 130)])
+@pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 3, 9, 1), (1, 3, 1, 21), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17),
+                                     (2, 3, 7, 130)])
 def test_edge_shapes_vs_oracle(lens, rf50mm_weights, N, C, H, W):
     g = torch.Generator().manual_seed(N * 1000 + H * 10 + W)
     img = torch.rand(N, C, H, W, generator=g)
