@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         // (short first hand-off); every other chunk is written by the 4 warps of one column half.
         // Fast mode (kslab 2) hands over 64-column chunks written by all 8 warps.
         for (int j = 0; j < 8; ++j)
-            mbar_init(bar_aready(j), (P.kslab == 2 || j < 2) ? TC_EPI_WARPS : TC_EPI_WARPS / 2);
+            // 3-term modes: barrier 0, 1 = 32-column chunks 0, 1 (all 8 warps, 16-column steps); barrier 2 = chunks
+            // 2+3 and barrier 4 = chunks 4..7 (the MMA warp is slower than the epilogue by then, so it only
+            // checks at K-steps 0, 1, 2 and 4: every spared wait is ~90 cycles of idle tensor pipe)
+            mbar_init(bar_aready(j), (P.kslab == 2 || j < 4) ? TC_EPI_WARPS : 2 * TC_EPI_WARPS);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
         fence_mbar_init();
     }
@@ -277,7 +280,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         tr.ev(0x500 + kc);
                         mbar_wait(bar_full(stage), fphase);      // hi weight stage (prefetched long ago)
                         tr.ev(0x600 + kc);
-                        if (new_a) {                             // A chunk: 32 columns (kslab 1) or 64 (kslab 2)
+                        // A chunk: 64 columns per barrier in fast mode; barriers 0, 1, 2 (= chunks 2+3), 4 (= 4..7) else
+                        if (new_a && (kslab == 2 || it < 3 || it == 4)) {
                             mbar_wait(bar_aready(it), (aphase >> it) & 1);
                             aphase ^= 1u << it;
                             tr.ev(0x400 + kc);
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     if (!use_al && it + 1 < nit) {
                         tr.ev(0x500 + kc + kslab);
                         mbar_wait(bar_full(stage), fphase);
-                        if (new_a) {
+                        if (new_a && (kslab == 2 || it + 1 < 3 || it + 1 == 4)) {     // same barrier map as above
                             mbar_wait(bar_aready(it + 1), (aphase >> (it + 1)) & 1);
                             aphase ^= 1u << (it + 1);
                         }
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             epi_group8(&rr[j & 1][i * 8], bias + col + i * 8, a_hi, a_lo, col / 8 + i, a_row, need_lo);
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_aready(fine ? 2 * j + hh : j));
+                        if (lane == 0) mbar_arrive(bar_aready(fine ? (j == 1 ? 2 : 4) : j));
                     }
                     tr.ev(0xC00 + j);                        // columns of 64-group j handed to the MMA warp
                 }
