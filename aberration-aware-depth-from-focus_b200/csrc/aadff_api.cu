@@ -593,7 +593,7 @@ int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N
 
 int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps, int N, int epi_load,
                            uint64_t* out_cycles, int device) {
-    if (!mmas_per_commit || !out_cycles || n_patterns < 1 || n_patterns > 31) return fail(AADFF_E_INVALID, "bad args");
+    if (!mmas_per_commit || !out_cycles || n_patterns < 1 || n_patterns > 16) return fail(AADFF_E_INVALID, "bad args");
     DeviceGuard guard(device);
     if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
     int* d_m = nullptr;
@@ -601,12 +601,17 @@ int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps,
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_m), n_patterns * sizeof(int)));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_out), 64 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemcpy(d_m, mmas_per_commit, n_patterns * sizeof(int), cudaMemcpyHostToDevice));
-    const int smem = TC_A_PART_BYTES + 65536 + 64;
+    uint8_t* d_src = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_src), 65536));
+    CUDA_TRY(cudaMemset(d_src, 0, 65536));
+    CUDA_TRY(cudaMemset(d_out, 0, 64 * sizeof(unsigned long long)));
+    const int smem = TC_A_PART_BYTES + 65536 + 128;
     CUDA_TRY(cudaFuncSetAttribute(debug_mma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    debug_mma_timing_kernel<<<1, 128, smem>>>(d_out, n_patterns, d_m, reps, N, epi_load);
+    debug_mma_timing_kernel<<<1, 128, smem>>>(d_out, n_patterns, d_m, reps, N, epi_load, d_src);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out_cycles, d_out, n_patterns * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_cycles, d_out, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_src);
     cudaFree(d_m);
     cudaFree(d_out);
     return AADFF_OK;

@@ -699,7 +699,7 @@ debug_umma_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
 debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas_per_commit, int reps, int N,
-                        int epi_load) {
+                        int epi_load, const uint8_t* __restrict__ gsrc) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -707,7 +707,17 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
     const uint32_t bar_done = sbase + TC_A_PART_BYTES + 65536, bar_slab = bar_done + 8;
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + TC_A_PART_BYTES + 65536 + 32);
     for (int i = threadIdx.x; i < (TC_A_PART_BYTES + 65536) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-    if (threadIdx.x == 0) { mbar_init(bar_done, 1); mbar_init(bar_slab, 1); fence_mbar_init(); }
+    // epi_load: low 16 bits = competing TMEM reads; bit 16 = warp 1 streams 16 KB bulk copies (3 in flight)
+    // into smem like the weight producer; bit 17 = warps 2-3 stream 16-byte st.shared like the epilogue.
+    const int tmem_reads = epi_load & 0xFFFF;
+    const bool do_copy = (epi_load >> 16) & 1, do_sts = (epi_load >> 17) & 1;
+    const uint32_t bar_copy = bar_done + 64;                 // 4 barriers
+    volatile uint32_t* stop = slot + 1;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_done, 1); mbar_init(bar_slab, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar_copy + 8 * i, 1);
+        fence_mbar_init();
+    }
     if (warp == 0) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(slot)));
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -717,6 +727,7 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
     uint32_t done_phase = 0;
     for (int p = 0; p < n_patterns; ++p) {
         const int m = mmas_per_commit[p];
+        if (threadIdx.x == 0) *stop = 0;
         __syncthreads();
         if (warp == 0) {
             const uint32_t idesc = umma_idesc_f16_f32(128, N);
@@ -737,11 +748,43 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
             const long long t1 = clock64();
             mbar_wait(bar_done, done_phase);
             const long long t2 = clock64();
-            if (lane == 0) { out[p * 2] = t1 - t0; out[p * 2 + 1] = t2 - t0; }
-        } else if (epi_load) {
+            if (lane == 0) { out[p * 2] = t1 - t0; out[p * 2 + 1] = t2 - t0; *stop = 1; }
+        } else if (warp == 1 && do_copy) {
+            // 16 KB copies into the upper 48 KB of the B region, three in flight
+            unsigned long long n = 0;
+            uint32_t ph = 0;
+            if (lane == 0) {
+                for (int i = 0; i < 3; ++i) {
+                    mbar_arrive_expect_tx(bar_copy + 8 * i, 16384);
+                    bulk_g2s(b_sm + 16384 + 16384 * i, gsrc + 16384 * i, 16384, bar_copy + 8 * i);
+                }
+                while (!*stop) {
+                    for (int i = 0; i < 3; ++i) {
+                        mbar_wait(bar_copy + 8 * i, ph);
+                        mbar_arrive_expect_tx(bar_copy + 8 * i, 16384);
+                        bulk_g2s(b_sm + 16384 + 16384 * i, gsrc + 16384 * i, 16384, bar_copy + 8 * i);
+                        ++n;
+                    }
+                    ph ^= 1;
+                }
+                for (int i = 0; i < 3; ++i) mbar_wait(bar_copy + 8 * i, ph);
+                out[32 + p] = n * 16384ull;
+            }
+            __syncwarp();
+        } else if (warp >= 2 && do_sts) {
+            unsigned long long n = 0;
+            const uint32_t dst = a_sm + 32768 + (uint32_t)(threadIdx.x - 64) * 16;
+            while (!*stop) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" :: "r"(dst + (uint32_t)i * 1024u), "r"(0u) : "memory");
+                n += 8;
+            }
+            if (threadIdx.x == 64) out[48 + p] = n * 64ull * 16ull;
+        } else if (tmem_reads) {
             // competing TMEM reads from the other accumulator half, like a concurrent epilogue
             uint32_t rr[32];
-            for (int it = 0; it < epi_load; ++it) {
+            for (int it = 0; it < tmem_reads; ++it) {
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + (it & 7) * 32, rr);
                 tmem_ld_wait();
             }

@@ -112,7 +112,9 @@ int aadff_debug_trace_entries(void);
 /* What-if timing switches for the fused kernel (results become invalid): bit 0 = skip the weight
  * copies, bit 1 = skip the operand stores.  0 restores normal operation.                     */
 int aadff_debug_set_flags(int flags);
-/* Issue-cost microbenchmark of tcgen05.mma / tcgen05.commit (see tests/gpu_diag.py mma_timing). */
+/* Issue-cost microbenchmark of tcgen05.mma / tcgen05.commit (see tests/gpu_diag.py mma_timing);
+ * epi_load: low 16 bits = competing TMEM reads, bit 16 = competing bulk copies into smem, bit 17 =
+ * competing st.shared stream.  out_cycles must hold 64 entries.                                   */
 int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps, int N, int epi_load,
                            uint64_t* out_cycles, int device);
 

@@ -178,15 +178,18 @@ def stage_mma_timing():
     nat = aadff_b200.native
     pats = np.array([1, 2, 4, 6, 8, 16, 64], dtype=np.int32)
     reps = 16
+    # epi_load: low 16 bits = competing TMEM reads, bit 16 = bulk copies into smem, bit 17 = st.shared stream
     for N in (256, 128):
-        for epi in (0, 4000):
-            out = np.zeros(2 * len(pats), dtype=np.uint64)
+        for epi in (0, 4000, 1 << 16, 1 << 17):
+            out = np.zeros(64, dtype=np.uint64)
             nat.check(nat.lib.aadff_debug_mma_timing(ctypes.c_void_p(pats.ctypes.data), len(pats), reps, N, epi,
                                                      ctypes.c_void_p(out.ctypes.data), 0))
             for i, m in enumerate(pats):
                 tot = int(m) * reps
-                print(f"N={N} epi_load={epi} [{m:2d} MMA + commit] x{reps}: issue {out[2*i]/tot:7.1f} cyc/MMA, "
-                      f"retire {out[2*i+1]/tot:7.1f} cyc/MMA", flush=True)
+                cyc = float(out[2 * i + 1])
+                print(f"N={N} epi_load={epi:#x} [{m:2d} MMA + commit] x{reps}: issue {out[2*i]/tot:7.1f} cyc/MMA, "
+                      f"retire {out[2*i+1]/tot:7.1f} cyc/MMA; competing copy {out[32+i]/cyc:5.1f} B/clk, "
+                      f"st.shared {out[48+i]/cyc:5.1f} B/clk", flush=True)
 
 
 def stage_rows():
