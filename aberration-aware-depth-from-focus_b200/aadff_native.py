@@ -14,7 +14,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libaadff.so")
+LIB_PATH = os.environ.get("AADFF_LIB_PATH") or os.path.join(_HERE, "libaadff.so")   # override: experiments only
 HEADER = os.path.join(_REPO, "include", "aadff.h")
 
 MODE_PARITY, MODE_FAST, MODE_FP32, MODE_MIXED, MODE_ECON = 0, 1, 2, 3, 4

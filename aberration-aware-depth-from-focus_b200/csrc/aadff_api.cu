@@ -13,6 +13,7 @@
 #include "../../include/aadff.h"
 #include "fused_tc_kernel.cuh"
 #include "gather_kernel.cuh"
+#include "gather_coalesced_kernel.cuh"
 #include "mlp_fp32_kernel.cuh"
 #include "thinlens_kernel.cuh"
 #include "focus_kernel.cuh"
@@ -30,6 +31,32 @@ std::atomic<unsigned long long*> g_trace{nullptr};
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
+}
+
+// Template switch of the register-streaming gather: odd ks in 3..31, cn in {1, 3}.
+template <int KS, int CN>
+void launch_gc(int grid, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
+               int c0) {
+    const int smem = GatherCfg<KS>::SMEM_FLOATS(CN) * (int)sizeof(float);          // <= 34.8 KB
+    local_psf_coalesced_kernel<KS, CN><<<grid, GC_WARPS * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
+}
+template <int KS>
+bool launch_gc_ks(int ks, int cn, int grid, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C,
+                  int H, int W, int c0) {
+    if constexpr (KS > 31) {
+        return false;
+    } else {
+        if (ks == KS) {
+            if (cn == 3) launch_gc<KS, 3>(grid, st, img, psf, out, N, C, H, W, c0);
+            else launch_gc<KS, 1>(grid, st, img, psf, out, N, C, H, W, c0);
+            return true;
+        }
+        return launch_gc_ks<KS + 2>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
+    }
+}
+bool launch_gather_coalesced(int ks, int cn, int grid, cudaStream_t st, const float* img, const float* psf, float* out,
+                             int N, int C, int H, int W, int c0) {
+    return launch_gc_ks<3>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
 }
 
 #define CUDA_TRY(expr)                                                                          \
@@ -459,6 +486,22 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ks >= 3 && ks <= 31 && !(g_dbg_flags.load() & 128)) {
+        // register-streaming kernel (gather_coalesced_kernel.cuh): any W, any alignment
+        const long long tiles = (long long)N * ((H + GC_WARPS - 1) / GC_WARPS) * ((W + GC_TW - 1) / GC_TW);
+        if (tiles >= (1ll << 31)) return fail(AADFF_E_INVALID, "image batch too large for one launch");
+        const int grid = (int)std::min<long long>(tiles, sms);
+        int c0 = 0;
+        while (c0 < C) {
+            const int cn = (C - c0 >= 3) ? 3 : 1;
+            if (!launch_gather_coalesced(ks, cn, grid, st, img, psf, out, N, C, H, W, c0))
+                return fail(AADFF_E_INVALID, "unsupported kernel size");
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+            c0 += cn;
+        }
+        return AADFF_OK;
+    }
     const int kk = ks * ks;
     int P = 32;
     while (P > 4 && P * kk * 4 > GS_BUF_BYTES) P >>= 1;

@@ -85,6 +85,29 @@ def test_gather_golden(pkg, i):
     assert maxabs(out, T(g["out"])) < 5e-5 * int(g["ks"])
 
 
+@pytest.mark.parametrize("ks", list(range(3, 33, 2)))
+def test_gather_every_kernel_size_vs_oracle(pkg, ks):
+    """Register-streaming gather (gather_coalesced_kernel.cuh): every odd ks in 3..31, ragged W/H (partial groups,
+    partial tiles, rows beyond H), C = 1..5 (3-channel and 1-channel passes), against the oracle's direct definition
+    and against the cp.async.bulk streaming kernel (debug flag 128 routes around the new kernel)."""
+    from deeplens.render_psf import local_psf_render
+    gen = torch.Generator().manual_seed(100 + ks)
+    for (N, C, H, W) in [(2, 3, 19, 45), (1, 5, 33, 36), (1, 1, 5, 7), (1, 2, 16, 64)]:
+        img = torch.rand(N, C, H, W, generator=gen)
+        psf = torch.rand(N, H, W, ks, ks, generator=gen)
+        psf = psf / psf.sum((-1, -2), keepdim=True)
+        ref = orc.local_psf_render(img, psf, ks)
+        out = local_psf_render(img.cuda(), psf.cuda(), ks)
+        assert out.shape == ref.shape
+        assert maxabs(out, ref) < 2e-6, (ks, N, C, H, W)
+        pkg.native.lib.aadff_debug_set_flags(128)
+        try:
+            old = local_psf_render(img.cuda(), psf.cuda(), ks)
+        finally:
+            pkg.native.lib.aadff_debug_set_flags(0)
+        assert maxabs(old, ref) < 2e-6, (ks, N, C, H, W)
+
+
 def test_pred_golden(lens):
     g = load_golden("kat_a_pred.npz")
     psf = lens.pred(T(g["inp"]).cuda())
