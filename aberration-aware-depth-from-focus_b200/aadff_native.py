@@ -84,6 +84,9 @@ def _load() -> ctypes.CDLL:
     lib.aadff_thinlens_render_f32.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_float] * 5 + \
                                              [ctypes.c_int, ctypes.c_void_p]
     lib.aadff_debug_set_desc_swap.argtypes = [ctypes.c_int]
+    lib.aadff_debug_econ_round.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p]
+    lib.aadff_debug_econ_round.restype = ctypes.c_int
     lib.aadff_select_focus_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]
     for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32",

@@ -17,6 +17,7 @@
 #include "mlp_fp32_kernel.cuh"
 #include "thinlens_kernel.cuh"
 #include "focus_kernel.cuh"
+#include "econ_calib.h"
 
 using namespace aadff;
 
@@ -37,7 +38,12 @@ int fail(int code, const std::string& msg) {
 template <int KS, int CN>
 void launch_gc(int grid, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
                int c0) {
-    const int smem = GatherCfg<KS>::SMEM_FLOATS(CN) * (int)sizeof(float);          // <= 34.8 KB
+    constexpr int smem = GatherCfg<KS>::SMEM_FLOATS(CN) * (int)sizeof(float);      // <= 69.6 KB (ks = 31, 3 channels)
+    if (smem > 48 * 1024) {
+        static std::atomic<bool> attr_set{false};              // one flag per instantiation
+        if (!attr_set.exchange(true))
+            cudaFuncSetAttribute(local_psf_coalesced_kernel<KS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
     local_psf_coalesced_kernel<KS, CN><<<grid, GC_WARPS * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
 }
 template <int KS>
@@ -87,6 +93,7 @@ int upload(const std::vector<T>& h, T** d) {
 
 // W rows [n0, n0+N) x all K -> K/32 slabs, each (hi, lo), canonical no-swizzle K-major layout:
 // half index inside a slab = (k/8) * (N*8) + n*8 + (k%8)
+// (for the calibrated econ weights W already holds fp16 values: hi = W exactly, lo = 0 and never loaded)
 void pack_group(const float* W, int out_f, int in_f, int n0, int N, std::vector<__half>& dst) {
     for (int kc = 0; kc < in_f / TC_SLAB_K; ++kc) {
         for (int part = 0; part < 2; ++part) {
@@ -120,6 +127,7 @@ struct aadff_psfnet {
     float* d_bias_tc = nullptr;
     float* d_w0b0 = nullptr;
     TcGroup groups[TC_MAX_GROUPS]{};
+    uint32_t w_off_econ[TC_MAX_GROUPS]{};   // econ mode, 2-term groups: calibrated fp16 weights (econ_calib.h)
     int n_groups = 0, n_hidden = 0, n_bias = 0;
     // host-call workspace
     cudaStream_t ws_stream = nullptr, ws_copy_stream = nullptr;
@@ -246,6 +254,20 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         }
         h->n_groups = gi;
         h->n_bias = (int)bias_tc.size();
+        // econ mode: L5.. and the head run 2 terms (Ah*Wh + Al*Wh) on output-error-calibrated fp16 weights
+        {
+            std::vector<std::vector<float>> wq;
+            calibrate_econ(weights, biases, dims, n_layers, TC_ECON_FIRST_LAYER, wq);
+            for (int g2 = 0; g2 < h->n_groups; ++g2) {
+                const bool hidden = g2 < h->n_hidden;
+                const int l = hidden ? g2 + 1 : L;
+                h->w_off_econ[g2] = h->groups[g2].w_off;                  // plain rounding unless calibrated
+                if (l < TC_ECON_FIRST_LAYER || wq[l].empty()) continue;
+                h->w_off_econ[g2] = (uint32_t)(pack.size() * sizeof(__half));
+                if (hidden) pack_group(wq[l].data(), dims[l + 1], dims[l], 0, TC_HID, pack);
+                else pack_group(wq[l].data(), h->kk, TC_HID, h->groups[g2].tap0, h->groups[g2].N, pack);
+            }
+        }
         std::vector<float> w0b0(320);
         std::memcpy(w0b0.data(), weights[0], 256 * sizeof(float));
         std::memcpy(w0b0.data() + 256, biases[0], 64 * sizeof(float));
@@ -300,8 +322,11 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
         const bool hidden = i < h->n_hidden;
         P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1
                        : (mode == AADFF_MODE_MIXED && i >= 3) ? 1
-                       : (mode == AADFF_MODE_ECON && hidden && i >= 4) ? 2     // L5..L9: weights rounded to fp16
+                       : (mode == AADFF_MODE_ECON && i >= TC_ECON_FIRST_LAYER - 1) ? 2   // L5.. and the head: fp16 weights
                        : 3;
+        if (mode == AADFF_MODE_ECON && P.g[i].terms == 2 && !(g_dbg_flags.load() & 256))
+            P.g[i].w_off = h->w_off_econ[i];                   // calibrated rounding (debug flag 256: plain rounding)
+        (void)hidden;
     }
     P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
     P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
@@ -633,6 +658,14 @@ int aadff_debug_umma_gemm(const float* A, const float* B, float* D, int K, int N
     return AADFF_OK;
 }
 
+
+int aadff_debug_econ_round(const float* W, int N, int K, const float* A, int NC, float* out) {
+    if (!W || !A || !out || N < 1 || K < 1 || NC < 1) return fail(AADFF_E_INVALID, "bad args");
+    std::vector<float> a(A, A + (size_t)NC * K), q;
+    if (!gptq_round_fp16(W, N, K, a, NC, q)) return fail(AADFF_E_INVALID, "activation covariance is not positive definite");
+    std::memcpy(out, q.data(), q.size() * sizeof(float));
+    return AADFF_OK;
+}
 
 int aadff_debug_mma_timing(const int* mmas_per_commit, int n_patterns, int reps, int N, int epi_load,
                            uint64_t* out_cycles, int device) {

@@ -55,6 +55,14 @@ __device__ __forceinline__ void tc_fence_after_sync() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------- 4-byte async copy global -> shared (LDGSTS)
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- bulk copy global -> shared
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile(

@@ -39,7 +39,7 @@ WORKLOADS = {  # name: (N, S, H, W, ks, description)
 CKPT = os.path.join(ROOT, "tests", "golden", "rf50mm_PSFNet480x640_ks11.pkl")
 DTYPES = {"parity": "f32 via fp16 hi/lo split (3 tcgen05 terms, f32 accumulate)",
           "mixed": "fp16 split for 3 layers then single fp16 term (f32 accumulate)",
-          "econ": "fp16 hi/lo split, 3 terms (L1-L4, head) / 2 terms (L5-L9), f32 accumulate",
+          "econ": "fp16 hi/lo split, 3 terms (L1-L4) / 2 terms on calibrated fp16 weights (L5-L9, head), f32 accumulate",
           "fast": "f16 operands, f32 accumulate", "fp32": "f32"}
 
 
@@ -62,7 +62,7 @@ def executed_mma_flops_per_pixel(ks, mode):
     cores), head padded to a multiple of 16 columns, times the number of fp16 terms per layer."""
     head = (ks * ks + 15) // 16 * 16
     per_layer = [64 * 256] + [256 * 256] * 8 + [256 * head]
-    terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "econ": [3] * 4 + [2] * 5 + [3],
+    terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "econ": [3] * 4 + [2] * 6,
              "fp32": [0] * 10}[mode]
     return 2 * sum(t * m for t, m in zip(terms, per_layer))
 
@@ -299,7 +299,7 @@ def run_ours(args):
                          "kernel": "fused_psfnet_render_kernel", "kernel_ms": ms_kernel,
                          "algorithmic_flops_per_pixel_slice": flops_per_pixel(ks),
                          "executed_mma_terms": {"parity": 3, "fast": 1, "mixed": "3 for L1-L3, 1 after",
-                                                "econ": "3 for L1-L4 and head, 2 for L5-L9", "fp32": 0}[args.mode]},
+                                                "econ": "3 for L1-L4, 2 for L5-L9 and head (calibrated fp16 weights)", "fp32": 0}[args.mode]},
             "checksum": float(checksum),
         }
         if extra:

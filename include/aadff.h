@@ -34,8 +34,9 @@ extern "C" {
 #define AADFF_MODE_FAST 1   /* tcgen05, single fp16 term: max-abs <= 3e-2 on noise images, see DESIGN.md */
 #define AADFF_MODE_FP32 2   /* CUDA-core fp32 FFMA, operation-for-operation with the reference          */
 #define AADFF_MODE_MIXED 3  /* tcgen05, 3 terms for the first three MMA layers, 1 term afterwards        */
-#define AADFF_MODE_ECON 4   /* tcgen05, 3 terms for L1-L4 and the head, 2 terms (fp16-rounded weights) for
-                               L5-L9: 19 % fewer MMAs, max-abs <= 1e-4 with ~1.4x margin on noise images   */
+#define AADFF_MODE_ECON 4   /* tcgen05, 3 terms for L1-L4, 2 terms (Ah*Wh + Al*Wh) for L5.. and the head on fp16 weights
+                               whose rounding is calibrated at create time to minimise the layer's output error over
+                               the network's input box (csrc/econ_calib.h): 21 % fewer MMAs, max-abs 2e-5 .. 4e-5   */
 
 typedef struct aadff_psfnet* aadff_psfnet_t;
 
@@ -112,6 +113,9 @@ int aadff_debug_trace_entries(void);
 /* What-if timing switches for the fused kernel (results become invalid): bit 0 = skip the weight
  * copies, bit 1 = skip the operand stores.  0 restores normal operation.                     */
 int aadff_debug_set_flags(int flags);
+/* Host-only: the output-error-calibrated fp16 rounding used by AADFF_MODE_ECON (csrc/econ_calib.h) for one layer.
+ * W [N][K], A [NC][K] = sample input activations of the layer, out [N][K] = fp16-representable values.  No GPU. */
+int aadff_debug_econ_round(const float* W, int N, int K, const float* A, int NC, float* out);
 /* Issue-cost microbenchmark of tcgen05.mma / tcgen05.commit (see tests/gpu_diag.py mma_timing);
  * epi_load: low 16 bits = competing TMEM reads, bit 16 = competing bulk copies into smem, bit 17 =
  * competing st.shared stream.  out_cycles must hold 64 entries.                                   */

@@ -99,6 +99,30 @@ def stage_tc_fast():
     _tc("econ")
 
 
+def stage_econ():
+    """econ mode with the calibrated fp16 weights vs plain rounding (debug flag 256), incl. a noise image at c2 size
+    against the fp32 CUDA-core kernel."""
+    import torch
+    import aadff_b200
+    from oracle import focal_stack_oracle as orc
+    for flags in (0, 256):
+        aadff_b200.native.lib.aadff_debug_set_flags(flags)
+        print(f"--- econ, debug flags {flags} ({'plain fp16 rounding' if flags else 'calibrated rounding'})")
+        _tc("econ")
+        lens = _lens(mode="econ")
+        gen = torch.Generator().manual_seed(5)
+        img = torch.rand(1, 3, 512, 512, generator=gen).cuda()
+        _, dm = orc.synthetic_rgbd(1, 512, 512, seed=77)
+        dep = -dm.cuda() * 1e3
+        foc = -orc.synthetic_focus(dm, 5).cuda() * 1e3
+        out = lens.render_stack(img, dep, foc, mode="econ")
+        ref = lens.render_stack(img, dep, foc, mode="fp32")
+        par = lens.render_stack(img, dep, foc, mode="parity")
+        print(f"noise image 5x512x512: econ vs fp32 max {float((out - ref).abs().max()):.3e} mean "
+              f"{float((out - ref).abs().mean()):.3e}; parity vs fp32 max {float((par - ref).abs().max()):.3e}", flush=True)
+    aadff_b200.native.lib.aadff_debug_set_flags(0)
+
+
 def stage_tc_ks31():
     import torch
     from conftest import load_golden
@@ -241,7 +265,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--run":
         STAGES[sys.argv[2]]()
         sys.exit(0)
-    names = sys.argv[1:] or ["umma", "fp32", "tc_parity", "tc_fast", "tc_ks31", "speed", "rows", "mma_timing"]
+    names = sys.argv[1:] or ["umma", "fp32", "tc_parity", "tc_fast", "tc_ks31", "speed", "rows", "mma_timing", "econ"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a")
     for name in names:

@@ -114,6 +114,44 @@ def test_select_focus_dist_matches_reference_golden():
         select_focus_dist(d, 3)
 
 
+def test_econ_weight_calibration_host_side(pkg):
+    """csrc/econ_calib.h (econ mode's output-error-calibrated fp16 rounding) against a numpy restatement of the same
+    recurrence: results are fp16 values, agree with the restatement almost everywhere (a near-tie may round the other
+    way), and shrink the layer's output error several-fold compared with plain rounding.  Host code only: no GPU."""
+    import ctypes
+    rng = np.random.default_rng(0)
+    N, K, NC = 48, 64, 512
+    M = rng.standard_normal((6, K))
+
+    def acts(n):                                        # correlated, ReLU-like, like a hidden layer fed from 4 inputs
+        return np.maximum(rng.standard_normal((n, 6)) @ M + 0.02 * rng.standard_normal((n, K)), 0)
+    A = acts(NC).astype(np.float32)
+    W = (rng.standard_normal((N, K)) * 0.1).astype(np.float32)
+    out = np.zeros_like(W)
+    rc = pkg.native.lib.aadff_debug_econ_round(ctypes.c_void_p(W.ctypes.data), N, K, ctypes.c_void_p(A.ctypes.data), NC,
+                                               ctypes.c_void_p(out.ctypes.data))
+    assert rc == 0
+    assert np.array_equal(out, out.astype(np.float16).astype(np.float32))
+
+    def f16(x):
+        return x.astype(np.float16).astype(np.float64)
+    A64, W64 = A.astype(np.float64), W.astype(np.float64)
+    H = A64.T @ A64 / NC
+    H += 1e-6 * np.mean(np.diag(H)) * np.eye(K)
+    U = np.linalg.cholesky(np.linalg.inv(H)).T
+    Wc, Q = W64.copy(), np.zeros_like(W64)
+    for k in range(K):
+        Q[:, k] = f16(Wc[:, k])
+        err = (Wc[:, k] - Q[:, k]) / U[k, k]
+        Wc[:, k + 1:] -= np.outer(err, U[k, k + 1:])
+    assert np.mean(out == Q) > 0.98
+    At = acts(4096)                                     # fresh samples of the same distribution
+    e_plain = np.linalg.norm(At @ (W64 - f16(W64)).T)
+    e_cal = np.linalg.norm(At @ (W64 - out).T)
+    assert e_cal < 0.6 * e_plain, (e_cal, e_plain)
+    assert pkg.native.lib.aadff_debug_econ_round(None, N, K, None, NC, None) != 0
+
+
 def test_item_partition_is_exact_and_balanced(pkg):
     sh = pkg.sharding
     for N, S in [(16, 5), (1, 10), (3, 7), (1, 1)]:
