@@ -123,6 +123,61 @@ def stage_econ():
     aadff_b200.native.lib.aadff_debug_set_flags(0)
 
 
+def stage_eager_gpu():
+    """The "before" number of SURVEY.md section 8d: the reference's operator sequence (11 x linear, replicate pad,
+    unfold, C-fold PSF copy, multiply, sum -- deeplens/psfnet.py:424-441 + render_psf.py:96-107) as eager PyTorch on
+    the same B200, fp32 with TF32 off, one slice per call like the reference's scripts."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import focal_stack_oracle as orc
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "rf50mm_PSFNet480x640_ks11.pkl"), map_location="cpu")
+    Ws, bs = orc.split_state_dict(sd)
+    Ws, bs = [w.cuda() for w in Ws], [b.cuda() for b in bs]
+    ks = 11
+
+    def render_eager(img, depth, foc):
+        N, C, H, W = img.shape
+        x, y = torch.meshgrid(torch.linspace(-1, 1, W, device="cuda"), torch.linspace(1, -1, H, device="cuda"), indexing="xy")
+        z = ((depth.reshape(N, H, W) + 200.0) / (-19800.0)).clamp(0, 1)
+        fz = ((foc.view(N, 1, 1) + 200.0) / (-19800.0)).clamp(0, 1).expand(N, H, W)
+        h = torch.stack((x.expand(N, H, W), y.expand(N, H, W), z, fz), -1)
+        for l, (Wl, bl) in enumerate(zip(Ws, bs)):
+            h = F.linear(h, Wl, bl)
+            h = torch.relu_(h) if l < len(Ws) - 1 else torch.sigmoid(h)
+        psf = F.normalize(h, p=1, dim=-1)
+        pad = F.pad(img, (5, 5, 5, 5), mode="replicate")
+        cols = F.unfold(pad, (ks, ks)).view(N, C, ks * ks, H * W)
+        taps = torch.stack(C * [psf.reshape(-1, ks, ks)], 1).view(N, H * W, C, ks * ks).permute(0, 2, 3, 1)
+        return (cols * taps).sum(2).view(N, C, H, W)
+
+    for name, (N, S, H, W) in (("c1", (1, 1, 480, 640)), ("c2", (1, 5, 512, 512)), ("c3", (16, 5, 256, 256))):
+        img, dm = orc.synthetic_rgbd(N, H, W, seed=1234)
+        foc = -orc.synthetic_focus(dm, max(S, 2)).cuda() * 1e3
+        img, dep = img.cuda(), -dm.cuda() * 1e3
+        lens = _lens(mode="parity")
+        with torch.no_grad():
+            ref0 = render_eager(img, dep, foc[:, 0].contiguous())
+            ours0 = lens.render(img, dep, foc[:, 0].contiguous())
+            err = float((ref0 - ours0).abs().max())
+            for _ in range(2):
+                for s in range(S):
+                    render_eager(img, dep, foc[:, s].contiguous())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 5
+            e0.record()
+            for _ in range(iters):
+                out = torch.stack([render_eager(img, dep, foc[:, s].contiguous()) for s in range(S)], dim=2)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"eager PyTorch on B200, {name} {N}x{S}x{H}x{W} k11: {ms:.2f} ms per stack  "
+              f"{N * S * H * W / ms / 1e3:.1f} Mpix*slices/s; peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; "
+              f"|eager - ours(parity)| max {err:.2e}", flush=True)
+
+
 def stage_tc_ks31():
     import torch
     from conftest import load_golden
