@@ -218,12 +218,21 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const int kslab = P.kslab;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
                 for (int it = 0; it < nit; ++it) {
+                    // 3-term groups, 4-stage ring: the hi and the lo slab of a K-slab complete ONE barrier (the hi
+                    // stage's), so the MMA warp pays one barrier wait per K-slab; the lo stage's own barrier only gets
+                    // a plain arrive to keep its phase in step with the ring
+                    uint32_t pair_bar = 0;
                     for (int part = 0; part < nparts; ++part) {
                         mbar_wait(bar_empty(stage), phase ^ 1);
                         tr.ev(0x100 + gi);                       // stage load issued
+                        if (part == 0) pair_bar = bar_full(stage);
                         if (elect_one_sync()) {
                             if (P.dbg & 1) {
                                 mbar_arrive(bar_full(stage));
+                            } else if (nparts == 2 && P.n_stages >= 4) {
+                                if (part == 0) mbar_arrive_expect_tx(pair_bar, 2 * bytes);
+                                else mbar_arrive(bar_full(stage));
+                                bulk_g2s(stage_addr(stage), src + (size_t)(it * 2 + part) * bytes, bytes, pair_bar);
                             } else {
                                 mbar_arrive_expect_tx(bar_full(stage), bytes * kslab);
                                 for (int hs = 0; hs < kslab; ++hs)
@@ -289,6 +298,53 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     }
                     tc_fence_after_sync();
                     const int hi_stage = stage;
+                    const bool last = (it + 1 == nit);
+                    if (use_al) {
+                        // ---- 2-/3-term groups (kslab == 1): ONE elected block per K-slab -- every extra elect / syncwarp /
+                        //      barrier probe in this warp delays the next MMA (its instruction stream is the critical path)
+                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                        const bool merged = three && P.n_stages >= 4;       // lo bytes arrived with the pair barrier
+                        if (elect_one_sync()) {
+                            const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
+                            umma_f16_ss(d_tmem, ah, db, idesc, it != 0);
+                            umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
+                            umma_f16_ss(d_tmem, al, db, idesc, 1);
+                            umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
+                            if (!three) {
+                                if (last) umma_commit(bar_accfull(buf));
+                                umma_commit(bar_empty(hi_stage));
+                            } else {
+                                umma_commit(bar_empty(hi_stage));           // release the hi stage early (64 KB ring)
+                                if (merged) {
+                                    const uint64_t dl = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
+                                    umma_f16_ss(d_tmem, ah, dl, idesc, 1);              // Ah*Wl
+                                    umma_f16_ss(d_tmem, ah + KSTEP_A, dl + kstep_b, idesc, 1);
+                                    if (last) umma_commit(bar_accfull(buf));
+                                    umma_commit(bar_empty(stage));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (three) {
+                            if (!merged) {
+                                // short ring (large kernel sizes): one barrier per stage, so that the hi MMAs above run
+                                // while the lo slab is still loading
+                                mbar_wait(bar_full(stage), fphase);
+                                tc_fence_after_sync();
+                                if (elect_one_sync()) {
+                                    const uint64_t dl = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
+                                    umma_f16_ss(d_tmem, ah, dl, idesc, 1);
+                                    umma_f16_ss(d_tmem, ah + KSTEP_A, dl + kstep_b, idesc, 1);
+                                    if (last) umma_commit(bar_accfull(buf));
+                                    umma_commit(bar_empty(stage));
+                                }
+                                __syncwarp();
+                            }
+                            if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                        }
+                        continue;
+                    }
+                    // ---- 1-term groups (fast / the tail of mixed)
                     if (elect_one_sync()) {
                         const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
                         umma_f16_ss(d_tmem, ah, db, idesc, it != 0);
@@ -297,33 +353,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             umma_f16_ss(d_tmem, ah + 2 * KSTEP_A, db + STAGE_STEP, idesc, 1);
                             umma_f16_ss(d_tmem, ah + 3 * KSTEP_A, db + STAGE_STEP + kstep_b, idesc, 1);
                         }
-                        if (use_al) {
-                            umma_f16_ss(d_tmem, al, db, idesc, 1);
-                            umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
-                            if (three) umma_commit(bar_empty(hi_stage));   // release the hi stage early: the 3-term
-                        }                                        // ring is only 64 KB deep, 4 MMAs cover the stall
                     }
                     __syncwarp();
                     if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
-                    int last_stage = hi_stage;
-                    if (three) {
-                        // ---- lo weight slab: Ah*Wl
-                        mbar_wait(bar_full(stage), fphase);
-                        tc_fence_after_sync();
-                        last_stage = stage;
-                        if (elect_one_sync()) {
-                            const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(last_stage) & 0x3FFFFu) >> 4);
-                            umma_f16_ss(d_tmem, ah, db, idesc, 1);
-                            umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
-                        }
-                        __syncwarp();
-                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
-                    }
-                    // ---- waits of the next step, while the MMAs above execute
-                    //      (fast mode only: in the 3-term modes the MMA warp runs ahead of the epilogue for the first
-                    //      chunks, and waiting for the next A chunk here would hold back the stage release)
+                    // ---- waits of the next step, while the MMAs above execute (before the commit that drains the pipe)
                     pre_waited = false;
-                    if (!use_al && it + 1 < nit) {
+                    if (it + 1 < nit) {
                         tr.ev(0x500 + kc + kslab);
                         mbar_wait(bar_full(stage), fphase);
                         if (new_a && (kslab == 2 || it + 1 < 3 || it + 1 == 4)) {     // same barrier map as above
@@ -335,8 +370,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     }
                     // ---- now the draining commit(s)
                     if (elect_one_sync()) {
-                        if (it + 1 == nit) umma_commit(bar_accfull(buf));   // the epilogue is waiting for this one
-                        umma_commit(bar_empty(last_stage));
+                        if (last) umma_commit(bar_accfull(buf));
+                        umma_commit(bar_empty(hi_stage));
                     }
                     __syncwarp();
                 }
