@@ -112,6 +112,18 @@ void pack_group(const float* W, int out_f, int in_f, int n0, int N, std::vector<
     }
 }
 
+// Bias slab of a hidden group: B[n][k], k < 16, canonical K-major layout; k = 0 holds fp16(b_n), k = 1 the fp16
+// remainder.  Multiplied by the constant A operand (ones in K columns 0 and 1) it starts the accumulator at b_n.
+void pack_bias_slab(const float* bias, int N, std::vector<__half>& dst) {
+    const size_t base = dst.size();
+    dst.resize(base + (size_t)N * 16, __float2half_rn(0.f));
+    for (int n = 0; n < N; ++n) {
+        const __half hi = __float2half_rn(bias[n]);
+        dst[base + (size_t)n * 8 + 0] = hi;
+        dst[base + (size_t)n * 8 + 1] = __float2half_rn(bias[n] - __half2float(hi));
+    }
+}
+
 }  // namespace
 
 struct aadff_psfnet {
@@ -128,7 +140,7 @@ struct aadff_psfnet {
     float* d_w0b0 = nullptr;
     TcGroup groups[TC_MAX_GROUPS]{};
     uint32_t w_off_econ[TC_MAX_GROUPS]{};   // econ mode, 2-term groups: calibrated fp16 weights (econ_calib.h)
-    int n_groups = 0, n_hidden = 0, n_bias = 0;
+    int n_groups = 0, n_hidden = 0, n_bias = 0, head_bias0 = 0;
     // host-call workspace
     cudaStream_t ws_stream = nullptr, ws_copy_stream = nullptr;
     std::vector<cudaEvent_t> ws_events;
@@ -231,12 +243,14 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
             g.bias_off = (uint16_t)bias_tc.size();
             g.new_a = 1;
             g.tap0 = 0;
+            pack_bias_slab(biases[l], TC_HID, pack);        // first slab of every hidden group
             pack_group(weights[l], dims[l + 1], dims[l], 0, TC_HID, pack);
             bias_tc.insert(bias_tc.end(), biases[l], biases[l] + TC_HID);
         }
         h->n_hidden = gi;
         const int L = n_layers - 1;
         const int head_bias0 = (int)bias_tc.size();
+        h->head_bias0 = head_bias0;
         bias_tc.resize(head_bias0 + nh_pad, 0.f);
         // head bias is stored pre-scaled by -log2(e): the kernel evaluates exp(-(acc+b)) as ex2(fma(acc,-log2e,b'))
         for (int n = 0; n < h->kk; ++n) bias_tc[head_bias0 + n] = -1.4426950408889634f * biases[L][n];
@@ -264,7 +278,10 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
                 h->w_off_econ[g2] = h->groups[g2].w_off;                  // plain rounding unless calibrated
                 if (l < TC_ECON_FIRST_LAYER || wq[l].empty()) continue;
                 h->w_off_econ[g2] = (uint32_t)(pack.size() * sizeof(__half));
-                if (hidden) pack_group(wq[l].data(), dims[l + 1], dims[l], 0, TC_HID, pack);
+                if (hidden) {
+                    pack_bias_slab(biases[l], TC_HID, pack);
+                    pack_group(wq[l].data(), dims[l + 1], dims[l], 0, TC_HID, pack);
+                }
                 else pack_group(wq[l].data(), h->kk, TC_HID, h->groups[g2].tap0, h->groups[g2].N, pack);
             }
         }
@@ -316,6 +333,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.n_groups = h->n_groups;
     P.n_hidden = h->n_hidden;
     P.n_bias = h->n_bias;
+    P.bias_skip = h->head_bias0;                               // hidden biases live in the bias slabs
     P.kk = h->kk;
     for (int i = 0; i < h->n_groups; ++i) {
         P.g[i] = h->groups[i];
@@ -341,7 +359,9 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.dbg = (uint32_t)g_dbg_flags.load();
     // shared-memory carve-up
     const uint32_t halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 16;   // float4 per pixel
-    const uint32_t fixed = 2 * TC_A_PART_BYTES + (uint32_t)h->n_bias * 4 + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES;
+    const uint32_t bias_bytes = (uint32_t)(h->n_bias - h->head_bias0) * 4;                 // head bias only
+    const uint32_t ones_bytes = 2 * TC_A_LBO;                                              // constant A operand of the bias slabs
+    const uint32_t fixed = 2 * TC_A_PART_BYTES + bias_bytes + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES + ones_bytes + 16;
     int stages = 4;
     while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;
     if (stages < 2) return fail(AADFF_E_UNSUPPORTED, "shared memory budget exceeded for this kernel size / channel count");
@@ -349,11 +369,12 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     for (int i = 0; i < h->n_groups; ++i) any_lo |= (P.g[i].terms >= 2);
     P.off_stage = 2 * TC_A_PART_BYTES;
     P.off_bias = P.off_stage + stages * TC_STAGE_BYTES;
-    P.off_w0 = P.off_bias + (uint32_t)h->n_bias * 4;
+    P.off_w0 = P.off_bias + bias_bytes;
     P.off_halo = P.off_w0 + 320 * 4;
     P.off_red = P.off_halo + halo_bytes;
     P.off_bar = P.off_red + TC_M * 5 * 4;
-    const uint32_t smem = P.off_bar + TC_BAR_BYTES;
+    P.off_ones = (P.off_bar + TC_BAR_BYTES + 15u) & ~15u;
+    const uint32_t smem = P.off_ones + ones_bytes;
     // no layer needs lo operands (fast mode): the A_lo region doubles the ring to 128 KB, organised as four
     // 32 KB stages (two packed K=32 slabs each) so that every issue iteration queues four MMAs
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;

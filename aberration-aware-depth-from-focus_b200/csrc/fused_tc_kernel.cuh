@@ -73,11 +73,13 @@ struct TcParams {
     TcGroup g[TC_MAX_GROUPS];
     int n_groups, n_hidden; // n_hidden = 9 (L1..L9); the rest are head blocks
     int n_bias, n_stages, kk;
+    int bias_skip;          // floats of the bias table that never go to shared memory: the hidden layers' biases are added
+                            // by the tensor core (first slab of every hidden group = a K=16 "bias slab", see below)
     int kslab;              // packed K=32 slabs per ring stage: 1 (any 3-term layer) or 2 (fast mode, 32 KB stages)
     int tiles_x, tiles_y;
     long long n_tiles;
     // shared-memory byte offsets
-    uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar;
+    uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar, off_ones;
     uint32_t dbg;           // what-if timing switches (results invalid): 1 = no weight copies, 2 = no A stores
     // pred mode (kernel instantiated with PRED = true): probes [M,4] in, L1-normalised PSFs [M, ks*ks] out
     const float* probes;
@@ -115,6 +117,13 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// fp16x2(max(a,0), max(b,0)) in one instruction (F2FP.RELU): ReLU costs nothing where only the hi part is needed
+__device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // upper half <- first source
+    return r;
+}
+
 // v[8] (fp32) -> fp16 hi (and lo = fp16(v - hi)) -> one 16-byte row of a K-major core matrix
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_hi, uint32_t addr_lo, bool need_lo) {
     uint32_t h[4];
@@ -132,20 +141,20 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_
     }
 }
 
-// 8 accumulator columns -> +bias, ReLU, fp16 hi/lo split -> one 16-byte operand row (K-group `kg`)
-__device__ __forceinline__ void epi_group8(const uint32_t* acc, const float* bias, uint32_t a_hi, uint32_t a_lo,
+// 8 accumulator columns -> ReLU, fp16 hi/lo split -> one 16-byte operand row (K-group `kg`)
+// (the bias is already in the accumulator: it was put there by the group's bias-slab MMA)
+__device__ __forceinline__ void epi_group8(const uint32_t* acc, uint32_t a_hi, uint32_t a_lo,
                                            uint32_t kg, uint32_t a_row, bool need_lo) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + 4);
+    if (!need_lo) {                          // single-term consumer: ReLU folded into the conversion
+        uint32_t h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = pack_half2_relu(__uint_as_float(acc[2 * u]), __uint_as_float(acc[2 * u + 1]));
+        st_shared_v4(a_hi + kg * TC_A_LBO + a_row, h[0], h[1], h[2], h[3]);
+        return;
+    }
     float v[8];
-    v[0] = fmaxf(__uint_as_float(acc[0]) + b0.x, 0.f);
-    v[1] = fmaxf(__uint_as_float(acc[1]) + b0.y, 0.f);
-    v[2] = fmaxf(__uint_as_float(acc[2]) + b0.z, 0.f);
-    v[3] = fmaxf(__uint_as_float(acc[3]) + b0.w, 0.f);
-    v[4] = fmaxf(__uint_as_float(acc[4]) + b1.x, 0.f);
-    v[5] = fmaxf(__uint_as_float(acc[5]) + b1.y, 0.f);
-    v[6] = fmaxf(__uint_as_float(acc[6]) + b1.z, 0.f);
-    v[7] = fmaxf(__uint_as_float(acc[7]) + b1.w, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = fmaxf(__uint_as_float(acc[u]), 0.f);
     const uint32_t off = kg * TC_A_LBO + a_row;
     store_split8(v, a_hi + off, a_lo + off, need_lo);
 }
@@ -197,7 +206,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < P.n_bias; i += TC_NT) s_bias[i] = __ldg(P.bias + i);
+    for (int i = threadIdx.x; i < P.n_bias - P.bias_skip; i += TC_NT) s_bias[i] = __ldg(P.bias + P.bias_skip + i);
+    // constant A operand of the bias slabs: [128 rows x K=16], columns 0 and 1 = 1.0, so that one MMA with the
+    // slab B[n][0] = fp16(b_n), B[n][1] = fp16(b_n - B[n][0]) starts the accumulator at the layer's bias
+    for (int i = threadIdx.x; i < 2 * TC_M; i += TC_NT) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i < TC_M) v.x = 0x3C003C00u;                      // halves (1.0, 1.0) in K columns 0, 1
+        *reinterpret_cast<uint4*>(smem + P.off_ones + (i < TC_M ? 0 : TC_A_LBO) + (i % TC_M) * 16) = v;
+    }
+    fence_proxy_async_smem();
     for (int i = threadIdx.x; i < 320; i += TC_NT) s_w0[i] = __ldg(P.w0b0 + i);
     if (warp == TC_WARP_PRODUCER) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     tc_fence_before_sync();
@@ -217,6 +234,21 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint8_t* src = P.wpack + P.g[gi].w_off;
                 const int kslab = P.kslab;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
+                if (gi < P.n_hidden) {                           // bias slab: N x 16 halves, one ring stage
+                    const uint32_t bbytes = (uint32_t)P.g[gi].N * 32;
+                    mbar_wait(bar_empty(stage), phase ^ 1);
+                    if (elect_one_sync()) {
+                        if (P.dbg & 1) {
+                            mbar_arrive(bar_full(stage));
+                        } else {
+                            mbar_arrive_expect_tx(bar_full(stage), bbytes);
+                            bulk_g2s(stage_addr(stage), src, bbytes, bar_full(stage));
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
+                    src += bbytes;
+                }
                 for (int it = 0; it < nit; ++it) {
                     // 3-term groups, 4-stage ring: the hi and the lo slab of a K-slab complete ONE barrier (the hi
                     // stage's), so the MMA warp pays one barrier wait per K-slab; the lo stage's own barrier only gets
@@ -255,6 +287,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         // descriptors: everything but the 14-bit start-address field (16-byte units) is loop invariant
         const uint64_t da_hi = umma_smem_desc(a_hi, TC_A_LBO, 128);
         const uint64_t da_lo = umma_smem_desc(a_lo, TC_A_LBO, 128);
+        const uint64_t da_ones = umma_smem_desc(sbase + P.off_ones, TC_A_LBO, 128);
         constexpr uint32_t KSTEP_A = (2 * TC_A_LBO) >> 4;            // one K=16 step of A
         constexpr uint32_t STAGE_STEP = TC_STAGE_BYTES >> 4;
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -280,6 +313,20 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 // that drains the pipe, so they overlap MMA execution instead of idling the tensor pipe.
                 const int kslab = P.kslab;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
+                const bool has_bias = gi < P.n_hidden;
+                if (has_bias) {
+                    // accumulator := bias (one MMA, constant A operand): needs no activations, so it is issued before
+                    // the first a_ready wait and runs inside the hand-off bubble between two layers
+                    mbar_wait(bar_full(stage), fphase);
+                    tc_fence_after_sync();
+                    if (elect_one_sync()) {
+                        const uint64_t dbb = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
+                        umma_f16_ss(d_tmem, da_ones, dbb, idesc, 0);
+                        umma_commit(bar_empty(stage));
+                    }
+                    __syncwarp();
+                    if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                }
                 bool pre_waited = false;
                 for (int it = 0; it < nit; ++it) {
                     const int kc = it * kslab;                   // first K=32 slab of this step
@@ -306,7 +353,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         const bool merged = three && P.n_stages >= 4;       // lo bytes arrived with the pair barrier
                         if (elect_one_sync()) {
                             const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
-                            umma_f16_ss(d_tmem, ah, db, idesc, it != 0);
+                            umma_f16_ss(d_tmem, ah, db, idesc, has_bias || it != 0);
                             umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
                             umma_f16_ss(d_tmem, al, db, idesc, 1);
                             umma_f16_ss(d_tmem, al + KSTEP_A, db + kstep_b, idesc, 1);
@@ -347,7 +394,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     // ---- 1-term groups (fast / the tail of mixed)
                     if (elect_one_sync()) {
                         const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
-                        umma_f16_ss(d_tmem, ah, db, idesc, it != 0);
+                        umma_f16_ss(d_tmem, ah, db, idesc, has_bias || it != 0);
                         umma_f16_ss(d_tmem, ah + KSTEP_A, db + kstep_b, idesc, 1);
                         if (kslab == 2) {
                             umma_f16_ss(d_tmem, ah + 2 * KSTEP_A, db + STAGE_STEP, idesc, 1);
@@ -508,7 +555,6 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 tc_fence_after_sync();
                 tr.ev(0xB00 + gi);                           // accumulator gi complete
                 const bool need_lo = P.g[gi + 1].terms >= 2;
-                const float* bias = s_bias + P.g[gi].bias_off;
                 const uint32_t t_acc = t_lane + buf * 256;
                 uint32_t rr[2][32], rf[2][16];
                 if (fine) {
@@ -527,7 +573,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             const int col = c * 32 + hh * 16;
 #pragma unroll
                             for (int i = 0; i < 2; ++i)
-                                epi_group8(&rf[c][i * 8], bias + col + i * 8, a_hi, a_lo, col / 8 + i, a_row, need_lo);
+                                epi_group8(&rf[c][i * 8], a_hi, a_lo, col / 8 + i, a_row, need_lo);
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(bar_aready(c));
@@ -536,7 +582,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         const int col = j * 64 + hh * 32;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            epi_group8(&rr[j & 1][i * 8], bias + col + i * 8, a_hi, a_lo, col / 8 + i, a_row, need_lo);
+                            epi_group8(&rr[j & 1][i * 8], a_hi, a_lo, col / 8 + i, a_row, need_lo);
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_aready(fine ? (j == 1 ? 2 : 4) : j));
@@ -572,7 +618,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     tr.ev(0x900);
                 }
                 const int gN = P.g[gi].N, gtap0 = P.g[gi].tap0;
-                const float* bias = s_bias + P.g[gi].bias_off;
+                const float* bias = s_bias + (P.g[gi].bias_off - P.bias_skip);
 #pragma unroll 1
                 for (int c32 = hh * 32; c32 < gN; c32 += 64) {
                     uint32_t rr[32];
