@@ -124,6 +124,15 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
     return r;
 }
 
+// hi half of the ReLU'd split with round-toward-zero: hi <= max(a, 0), so that the remainder a - hi is >= 0 for a > 0
+// and < 0 exactly when a < 0 (hi = 0) -- a second cvt.relu then yields lo without an explicit max().  The pair
+// (hi, lo) carries 21 bits instead of the 22 of a round-to-nearest split; both are far below the 1e-4 budget.
+__device__ __forceinline__ uint32_t pack_half2_relu_rz(float a, float b) {
+    uint32_t r;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
 // v[8] (fp32) -> fp16 hi (and lo = fp16(v - hi)) -> one 16-byte row of a K-major core matrix
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint32_t addr_hi, uint32_t addr_lo, bool need_lo) {
     uint32_t h[4];
@@ -152,11 +161,18 @@ __device__ __forceinline__ void epi_group8(const uint32_t* acc, uint32_t a_hi, u
         st_shared_v4(a_hi + kg * TC_A_LBO + a_row, h[0], h[1], h[2], h[3]);
         return;
     }
-    float v[8];
+    // hi/lo consumer: hi = rz(relu(a)), lo = rn(relu(a - hi))
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = fmaxf(__uint_as_float(acc[u]), 0.f);
+    for (int u = 0; u < 4; ++u) {
+        const float a0 = __uint_as_float(acc[2 * u]), a1 = __uint_as_float(acc[2 * u + 1]);
+        h[u] = pack_half2_relu_rz(a0, a1);
+        const float2 f = __half22float2(*reinterpret_cast<__half2*>(&h[u]));
+        l[u] = pack_half2_relu(a0 - f.x, a1 - f.y);
+    }
     const uint32_t off = kg * TC_A_LBO + a_row;
-    store_split8(v, a_hi + off, a_lo + off, need_lo);
+    st_shared_v4(a_hi + off, h[0], h[1], h[2], h[3]);
+    st_shared_v4(a_lo + off, l[0], l[1], l[2], l[3]);
 }
 
 // Warp roles.  The hardware warp arbiter favours the HIGHEST warp id on a scheduler, so the two
