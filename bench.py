@@ -64,7 +64,8 @@ def executed_mma_flops_per_pixel(ks, mode):
     per_layer = [64 * 256] + [256 * 256] * 8 + [256 * head]
     terms = {"parity": [3] * 10, "fast": [1] * 10, "mixed": [3, 3, 3] + [1] * 7, "econ": [3] * 4 + [2] * 6,
              "fp32": [0] * 10}[mode]
-    return 2 * sum(t * m for t, m in zip(terms, per_layer))
+    bias_slabs = 0 if mode == "fp32" else 9 * 16 * 256          # one K=16 bias-slab MMA per hidden layer L1..L9
+    return 2 * (sum(t * m for t, m in zip(terms, per_layer)) + bias_slabs)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` captures
@@ -73,17 +74,18 @@ NCU_TRAFFIC_BYTES = {("c2", "parity"): 6.57e6, ("c2", "fast"): 5.43e6}
 
 
 def weights_for(ks):
-    from oracle import focal_stack_oracle as orc
+    # data generators live in the product package (aadff_b200.synthetic); the oracle is imported only by the CPU arms
+    from aadff_b200 import synthetic
     if ks == 11:
-        return orc.split_state_dict(torch.load(CKPT, map_location="cpu"))
-    return orc.seeded_psfnet_weights(ks, seed=0)
+        return synthetic.split_state_dict(torch.load(CKPT, map_location="cpu"))
+    return synthetic.seeded_psfnet_weights(ks, seed=0)
 
 
 def make_inputs(name, rank):
-    from oracle import focal_stack_oracle as orc
+    from aadff_b200 import synthetic
     N, S, H, W, ks, _ = WORKLOADS[name]
-    img, depth_m = orc.synthetic_rgbd(N, H, W, seed=1234 + 17 * rank)
-    foc_m = orc.synthetic_focus(depth_m, S)
+    img, depth_m = synthetic.synthetic_rgbd(N, H, W, seed=1234 + 17 * rank)
+    foc_m = synthetic.synthetic_focus(depth_m, S)
     return img, -depth_m * 1e3, -foc_m * 1e3
 
 

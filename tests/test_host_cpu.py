@@ -152,6 +152,24 @@ def test_econ_weight_calibration_host_side(pkg):
     assert pkg.native.lib.aadff_debug_econ_round(None, N, K, None, NC, None) != 0
 
 
+def test_product_synthetic_generators_match_the_oracle_copies(pkg):
+    """bench.py's GPU arm draws its inputs from aadff_b200.synthetic, the CPU arms and the tests from the oracle's own
+    copy: both must give identical tensors (same workload on both arms, no oracle import in the product)."""
+    from aadff_b200 import synthetic
+    from oracle import focal_stack_oracle as orc
+    for (N, H, W, seed) in [(1, 48, 64, 1234), (2, 40, 56, 1251)]:
+        a, b = synthetic.synthetic_rgbd(N, H, W, seed), orc.synthetic_rgbd(N, H, W, seed)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        for S in (1, 2, 5, 10):
+            assert torch.equal(synthetic.synthetic_focus(a[1], S), orc.synthetic_focus(b[1], S))
+    for ks in (11, 31):
+        (Wa, ba), (Wb, bb) = synthetic.seeded_psfnet_weights(ks, 0), orc.seeded_psfnet_weights(ks, 0)
+        assert all(torch.equal(x, y) for x, y in zip(Wa, Wb)) and all(torch.equal(x, y) for x, y in zip(ba, bb))
+    sd = torch.load(os.path.join(GOLDEN, "rf50mm_PSFNet480x640_ks11.pkl"), map_location="cpu")
+    (Wa, ba), (Wb, bb) = synthetic.split_state_dict(sd), orc.split_state_dict(sd)
+    assert all(torch.equal(x, y) for x, y in zip(Wa, Wb)) and all(torch.equal(x, y) for x, y in zip(ba, bb))
+
+
 def test_item_partition_is_exact_and_balanced(pkg):
     sh = pkg.sharding
     for N, S in [(16, 5), (1, 10), (3, 7), (1, 1)]:
