@@ -267,19 +267,18 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 }
                 for (int it = 0; it < nit; ++it) {
                     // 3-term groups, 4-stage ring: the hi and the lo slab of a K-slab complete ONE barrier (the hi
-                    // stage's), so the MMA warp pays one barrier wait per K-slab; the lo stage's own barrier only gets
-                    // a plain arrive to keep its phase in step with the ring
+                    // stage's), so the MMA warp pays one barrier wait per K-slab; the lo stage's own barrier is not used in
+                    // that round (the MMA warp keeps one phase bit per stage barrier)
                     uint32_t pair_bar = 0;
                     for (int part = 0; part < nparts; ++part) {
                         mbar_wait(bar_empty(stage), phase ^ 1);
                         tr.ev(0x100 + gi);                       // stage load issued
                         if (part == 0) pair_bar = bar_full(stage);
                         if (elect_one_sync()) {
-                            if (P.dbg & 1) {
-                                mbar_arrive(bar_full(stage));
+                            if (P.dbg & 1) {                     // what-if: no copies (lo stages of a pair have no barrier use)
+                                if (!(nparts == 2 && P.n_stages >= 4 && part == 1)) mbar_arrive(bar_full(stage));
                             } else if (nparts == 2 && P.n_stages >= 4) {
                                 if (part == 0) mbar_arrive_expect_tx(pair_bar, 2 * bytes);
-                                else mbar_arrive(bar_full(stage));
                                 bulk_g2s(stage_addr(stage), src + (size_t)(it * 2 + part) * bytes, bytes, pair_bar);
                             } else {
                                 mbar_arrive_expect_tx(bar_full(stage), bytes * kslab);
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     } else if (warp == TC_WARP_MMA) {
         // =========================================================== MMA issuer (converged warp, elected lane)
         int stage = 0;
-        uint32_t fphase = 0, aphase = 0, frphase = 0;     // bit j / bit b = parity to wait for next
+        uint32_t fbits = 0, aphase = 0, frphase = 0;      // bit s / j / b = parity to wait for next on that barrier
         uint32_t gcount = 0;
         TcTrace<TRACE> tr; tr.init(lane == 0 ? P.trace : nullptr, 1);
         // descriptors: everything but the 14-bit start-address field (16-byte units) is loop invariant
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 if (has_bias) {
                     // accumulator := bias (one MMA, constant A operand): needs no activations, so it is issued before
                     // the first a_ready wait and runs inside the hand-off bubble between two layers
-                    mbar_wait(bar_full(stage), fphase);
+                    { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }
                     tc_fence_after_sync();
                     if (elect_one_sync()) {
                         const uint64_t dbb = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
@@ -341,7 +340,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         umma_commit(bar_empty(stage));
                     }
                     __syncwarp();
-                    if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                    if (++stage == P.n_stages) stage = 0;
                 }
                 bool pre_waited = false;
                 for (int it = 0; it < nit; ++it) {
@@ -350,7 +349,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
                     if (!pre_waited) {
                         tr.ev(0x500 + kc);
-                        mbar_wait(bar_full(stage), fphase);      // hi weight stage (prefetched long ago)
+                        { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }      // hi weight stage (prefetched long ago)
                         tr.ev(0x600 + kc);
                         // A chunk: 64 columns per barrier in fast mode; barriers 0, 1, 2 (= chunks 2+3), 4 (= 4..7) else
                         if (new_a && (kslab == 2 || it < 3 || it == 4)) {
@@ -365,7 +364,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     if (use_al) {
                         // ---- 2-/3-term groups (kslab == 1): ONE elected block per K-slab -- every extra elect / syncwarp /
                         //      barrier probe in this warp delays the next MMA (its instruction stream is the critical path)
-                        if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                        if (++stage == P.n_stages) stage = 0;
                         const bool merged = three && P.n_stages >= 4;       // lo bytes arrived with the pair barrier
                         if (elect_one_sync()) {
                             const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
@@ -392,7 +391,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             if (!merged) {
                                 // short ring (large kernel sizes): one barrier per stage, so that the hi MMAs above run
                                 // while the lo slab is still loading
-                                mbar_wait(bar_full(stage), fphase);
+                                { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }
                                 tc_fence_after_sync();
                                 if (elect_one_sync()) {
                                     const uint64_t dl = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
@@ -403,7 +402,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                                 }
                                 __syncwarp();
                             }
-                            if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                            if (++stage == P.n_stages) stage = 0;
                         }
                         continue;
                     }
@@ -418,12 +417,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         }
                     }
                     __syncwarp();
-                    if (++stage == P.n_stages) { stage = 0; fphase ^= 1; }
+                    if (++stage == P.n_stages) stage = 0;
                     // ---- waits of the next step, while the MMAs above execute (before the commit that drains the pipe)
                     pre_waited = false;
                     if (it + 1 < nit) {
                         tr.ev(0x500 + kc + kslab);
-                        mbar_wait(bar_full(stage), fphase);
+                        { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }
                         if (new_a && (kslab == 2 || it + 1 < 3 || it + 1 == 4)) {     // same barrier map as above
                             mbar_wait(bar_aready(it + 1), (aphase >> (it + 1)) & 1);
                             aphase ^= 1u << (it + 1);
