@@ -556,7 +556,7 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
         // HBM-streaming path: cp.async.bulk PSF chunks, smem halo tile.  One 16 KB chunk buffer per warp, 8 warps.
         // (Two buffers per warp only fit with 6 warps and measured 20 % slower: the kernel is limited by the
         //  arithmetic/latency of its 8 warps, not by exposed copy latency -- debug flag 64 selects that variant.)
-        const int nbuf = (P == 32 && g_dbg_flags.load() == 64) ? 2 : 1;
+        const int nbuf = (P == 32 && (g_dbg_flags.load() & 64)) ? 2 : 1;
         const int nw = (nbuf == 2) ? GS_TILE_H_2BUF : GS_TILE_H_1BUF;
         const int buf_bytes = (P * kk * 4 + 127) / 128 * 128;
         const int HH = nw + ks - 1, pitch = (GS_TILE_W + ks - 1) | 1;

@@ -110,8 +110,11 @@ int aadff_debug_set_desc_swap(int swap);
  * uint64 (zero-filled by the caller), NULL switches tracing off.  See tests/gpu_trace.py.    */
 int aadff_debug_set_trace(void* device_buffer);
 int aadff_debug_trace_entries(void);
-/* What-if timing switches for the fused kernel (results become invalid): bit 0 = skip the weight
- * copies, bit 1 = skip the operand stores.  0 restores normal operation.                     */
+/* Debug switches, 0 restores normal operation.  What-if timing of the fused kernel (results become invalid):
+ * bit 0 = skip the weight copies, bit 1 = skip the operand stores.  Cross-check paths (results stay valid):
+ * 128 = aadff_local_psf_render_f32 through the older cp.async.bulk streaming kernel instead of the register-
+ * streaming one (128 + 64: with two chunk buffers per warp), 256 = AADFF_MODE_ECON with plainly rounded fp16
+ * weights instead of the calibrated ones.                                                       */
 int aadff_debug_set_flags(int flags);
 /* Host-only: the output-error-calibrated fp16 rounding used by AADFF_MODE_ECON (csrc/econ_calib.h) for one layer.
  * W [N][K], A [NC][K] = sample input activations of the layer, out [N][K] = fp16-representable values.  No GPU. */
