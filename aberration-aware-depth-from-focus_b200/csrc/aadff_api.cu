@@ -296,12 +296,15 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         if (rc) { aadff_psfnet_destroy(h); return rc; }
         rc = upload(w0b0, &h->d_w0b0);
         if (rc) { aadff_psfnet_destroy(h); return rc; }
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        const int so = h->smem_optin;
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 0>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 1>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 3>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 0>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 1>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 3>, attr, so));
     }
     *out = h;
     return AADFF_OK;
@@ -380,12 +383,22 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;
     P.n_stages = (P.kslab == 2) ? 4 : stages;
     const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
-    if (P.probes != nullptr)
-        fused_psfnet_render_kernel<false, true><<<grid, TC_NT, smem, st>>>(P);
-    else if (P.trace != nullptr)
-        fused_psfnet_render_kernel<true, false><<<grid, TC_NT, smem, st>>>(P);
-    else
-        fused_psfnet_render_kernel<false, false><<<grid, TC_NT, smem, st>>>(P);
+    // kernel specialisation: 3 = all groups three-term (parity), 1 = all single-term with the long ring (fast),
+    // 0 = per-group terms (econ, mixed, short-ring fast, and the traced build)
+    bool all3 = true, all1 = true;
+    for (int i = 0; i < h->n_groups; ++i) { all3 &= (P.g[i].terms == 3); all1 &= (P.g[i].terms == 1); }
+    const int uni = (all3 && P.kslab == 1) ? 3 : (all1 && P.kslab == 2) ? 1 : 0;
+    if (P.trace != nullptr && P.probes == nullptr)
+        fused_psfnet_render_kernel<true, false, 0><<<grid, TC_NT, smem, st>>>(P);
+    else if (P.probes != nullptr) {
+        if (uni == 3) fused_psfnet_render_kernel<false, true, 3><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 1) fused_psfnet_render_kernel<false, true, 1><<<grid, TC_NT, smem, st>>>(P);
+        else fused_psfnet_render_kernel<false, true, 0><<<grid, TC_NT, smem, st>>>(P);
+    } else {
+        if (uni == 3) fused_psfnet_render_kernel<false, false, 3><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 1) fused_psfnet_render_kernel<false, false, 1><<<grid, TC_NT, smem, st>>>(P);
+        else fused_psfnet_render_kernel<false, false, 0><<<grid, TC_NT, smem, st>>>(P);
+    }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;

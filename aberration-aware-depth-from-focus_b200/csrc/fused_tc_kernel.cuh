@@ -182,8 +182,14 @@ __device__ __forceinline__ void epi_group8(const uint32_t* acc, uint32_t a_hi, u
 constexpr int TC_WARP_PRODUCER = TC_EPI_WARPS;       // warp 8
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;        // warp 9
 
-template <bool TRACE, bool PRED>
+// UNI specialises the kernel on the arithmetic of the whole network so that the mode-dependent branches disappear
+// from the issuing warps (whose instruction streams are the critical path): 3 = every group three terms, kslab 1
+// (parity); 1 = every group a single term, kslab 2 (fast with the 128 KB ring); 0 = per-group terms at run time
+// (econ, mixed, and fast when the ring is short).
+template <bool TRACE, bool PRED, int UNI>
 __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
+    const int kslab_c = UNI == 3 ? 1 : UNI == 1 ? 2 : P.kslab;
+    auto terms_of = [&](int gi) -> int { return UNI == 3 ? 3 : UNI == 1 ? 1 : (int)P.g[gi].terms; };
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     const uint32_t a_hi = sbase, a_lo = sbase + TC_A_PART_BYTES;
     const uint32_t stage0 = sbase + P.off_stage;
     // ring stage s: first four in the stage area, the rest (fast mode only) in the unused A_lo region
-    const int stage_bytes = P.kslab * TC_STAGE_BYTES, stages_in_area = 4 / P.kslab;
+    const int stage_bytes = kslab_c * TC_STAGE_BYTES, stages_in_area = 4 / kslab_c;
     auto stage_addr = [&](int st) {
         return st < stages_in_area ? stage0 + st * stage_bytes : a_lo + (st - stages_in_area) * stage_bytes;
     };
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             // 3-term modes: barrier 0, 1 = 32-column chunks 0, 1 (all 8 warps, 16-column steps); barrier 2 = chunks
             // 2+3 and barrier 4 = chunks 4..7 (the MMA warp is slower than the epilogue by then, so it only
             // checks at K-steps 0, 1, 2 and 4: every spared wait is ~90 cycles of idle tensor pipe)
-            mbar_init(bar_aready(j), (P.kslab == 2 || j < 4) ? TC_EPI_WARPS : 2 * TC_EPI_WARPS);
+            mbar_init(bar_aready(j), (kslab_c == 2 || j < 4) ? TC_EPI_WARPS : 2 * TC_EPI_WARPS);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
         fence_mbar_init();
     }
@@ -246,9 +252,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             for (int gi = 0; gi < P.n_groups; ++gi) {
                 const uint32_t bytes = (uint32_t)P.g[gi].N * (TC_SLAB_K * 2);
-                const int nparts = (P.g[gi].terms == 3) ? 2 : 1;
+                const int nparts = (terms_of(gi) == 3) ? 2 : 1;
                 const uint8_t* src = P.wpack + P.g[gi].w_off;
-                const int kslab = P.kslab;
+                const int kslab = kslab_c;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
                 if (gi < P.n_hidden) {                           // bias slab: N x 16 halves, one ring stage
                     const uint32_t bbytes = (uint32_t)P.g[gi].N * 32;
@@ -309,8 +315,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             for (int gi = 0; gi < P.n_groups; ++gi) {
                 const uint32_t gN = P.g[gi].N;
                 const int nkc = P.g[gi].K / TC_SLAB_K;
-                const bool three = P.g[gi].terms == 3;       // Ah*Wh + Al*Wh + Ah*Wl
-                const bool use_al = P.g[gi].terms >= 2;      // 2 terms: Ah*Wh + Al*Wh (weights rounded to fp16)
+                const bool three = terms_of(gi) == 3;        // Ah*Wh + Al*Wh + Ah*Wl
+                const bool use_al = terms_of(gi) >= 2;       // 2 terms: Ah*Wh + Al*Wh (weights rounded to fp16)
                 const bool new_a = P.g[gi].new_a != 0;
                 const uint32_t buf = gcount & 1;
                 if (gcount >= 2) {           // the epilogue must have drained group gcount-2
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 // Issue loop, software-pipelined by one step: the barrier waits of step it+1 (~90 cycles each even
                 // when already complete) are performed after the MMAs of step it are queued and BEFORE the commit
                 // that drains the pipe, so they overlap MMA execution instead of idling the tensor pipe.
-                const int kslab = P.kslab;
+                const int kslab = kslab_c;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
                 const bool has_bias = gi < P.n_hidden;
                 if (has_bias) {
@@ -458,7 +464,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         unsigned long long gcount = 0;
         TcTrace<TRACE> tr; tr.init((lane == 0 && (e == 0 || e == 7)) ? P.trace : nullptr, e == 0 ? 2 : 3);
         const float NEG_LOG2E = -1.4426950408889634f;
-        const bool fine = P.kslab == 1;         // 16-column first hand-offs (3-term modes)
+        const bool fine = kslab_c == 1;         // 16-column first hand-offs (3-term modes)
 
         // tile -> (image n, slice s, tile origin); depth / focus of this thread's pixel are fetched
         // one tile ahead so that layer 0 (the head of the serial chain) never waits on HBM
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 z = depth_to_z(nx_depth, ra.d_min, ra.d_range);
                 fz = depth_to_z(nx_foc, ra.d_min, ra.d_range);
             }
-            const bool need_lo = P.g[0].terms >= 2;
+            const bool need_lo = terms_of(0) >= 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 // K-group (8 features) computed in this step: a contiguous quarter in fast mode, half of
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 afphase ^= 1u << buf;
                 tc_fence_after_sync();
                 tr.ev(0xB00 + gi);                           // accumulator gi complete
-                const bool need_lo = P.g[gi + 1].terms >= 2;
+                const bool need_lo = terms_of(gi + 1) >= 2;
                 const uint32_t t_acc = t_lane + buf * 256;
                 uint32_t rr[2][32], rf[2][16];
                 if (fine) {
