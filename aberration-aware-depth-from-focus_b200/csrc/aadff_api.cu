@@ -301,6 +301,10 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 0>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 1>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 3>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 2>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 2>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 5>, attr, so));
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 5>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 0>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 1>, attr, so));
@@ -342,8 +346,8 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
         P.g[i] = h->groups[i];
         const bool hidden = i < h->n_hidden;
         P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1
-                       : (mode == AADFF_MODE_MIXED && i >= 3) ? 1
-                       : (mode == AADFF_MODE_ECON && i >= TC_ECON_FIRST_LAYER - 1) ? 2   // L5.. and the head: fp16 weights
+                       : (mode == AADFF_MODE_MIXED && i >= TC_MIXED_FIRST_GROUP) ? 1
+                       : (mode == AADFF_MODE_ECON && i >= TC_ECON_FIRST_GROUP) ? 2   // L5.. and the head: fp16 weights
                        : 3;
         if (mode == AADFF_MODE_ECON && P.g[i].terms == 2 && !(g_dbg_flags.load() & 256))
             P.g[i].w_off = h->w_off_econ[i];                   // calibrated rounding (debug flag 256: plain rounding)
@@ -387,15 +391,24 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     // 0 = per-group terms (econ, mixed, short-ring fast, and the traced build)
     bool all3 = true, all1 = true;
     for (int i = 0; i < h->n_groups; ++i) { all3 &= (P.g[i].terms == 3); all1 &= (P.g[i].terms == 1); }
-    const int uni = (all3 && P.kslab == 1) ? 3 : (all1 && P.kslab == 2) ? 1 : 0;
+    bool econ_pat = (P.kslab == 1);
+    for (int i = 0; i < h->n_groups; ++i) econ_pat &= (P.g[i].terms == (i < TC_ECON_FIRST_GROUP ? 3 : 2));
+    bool mixed_pat = (P.kslab == 1);
+    for (int i = 0; i < h->n_groups; ++i) mixed_pat &= (P.g[i].terms == (i < TC_MIXED_FIRST_GROUP ? 3 : 1));
+    static_assert(TC_ECON_FIRST_GROUP == TC_ECON_FIRST_LAYER - 1, "group g holds layer g + 1");
+    const int uni = (all3 && P.kslab == 1) ? 3 : (all1 && P.kslab == 2) ? 1 : econ_pat ? 2 : mixed_pat ? 5 : 0;
     if (P.trace != nullptr && P.probes == nullptr)
         fused_psfnet_render_kernel<true, false, 0><<<grid, TC_NT, smem, st>>>(P);
     else if (P.probes != nullptr) {
         if (uni == 3) fused_psfnet_render_kernel<false, true, 3><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 2) fused_psfnet_render_kernel<false, true, 2><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 5) fused_psfnet_render_kernel<false, true, 5><<<grid, TC_NT, smem, st>>>(P);
         else if (uni == 1) fused_psfnet_render_kernel<false, true, 1><<<grid, TC_NT, smem, st>>>(P);
         else fused_psfnet_render_kernel<false, true, 0><<<grid, TC_NT, smem, st>>>(P);
     } else {
         if (uni == 3) fused_psfnet_render_kernel<false, false, 3><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 2) fused_psfnet_render_kernel<false, false, 2><<<grid, TC_NT, smem, st>>>(P);
+        else if (uni == 5) fused_psfnet_render_kernel<false, false, 5><<<grid, TC_NT, smem, st>>>(P);
         else if (uni == 1) fused_psfnet_render_kernel<false, false, 1><<<grid, TC_NT, smem, st>>>(P);
         else fused_psfnet_render_kernel<false, false, 0><<<grid, TC_NT, smem, st>>>(P);
     }

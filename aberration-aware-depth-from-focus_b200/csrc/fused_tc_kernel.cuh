@@ -54,6 +54,8 @@ constexpr int TC_MAX_KS = 31;
 constexpr int TC_MAX_C = 4;
 constexpr int TC_BAR_BYTES = 256;        // mbarriers (2*8 + 4 + 2 + 2) * 8 B + TMEM slot
 constexpr int TC_TRACE_N = 4096;         // trace entries per role
+constexpr int TC_MIXED_FIRST_GROUP = 3;  // mixed: groups 0..2 (L1..L3) three terms, one term after
+constexpr int TC_ECON_FIRST_GROUP = 4;   // econ: groups 0..3 (L1..L4) three terms, L5.. and the head two (econ_calib.h)
 
 struct TcGroup {            // one accumulation group: one layer, or one <=256-column block of the head
     uint32_t w_off;         // byte offset of its first slab in the packed weights
@@ -185,11 +187,15 @@ constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;        // warp 9
 // UNI specialises the kernel on the arithmetic of the whole network so that the mode-dependent branches disappear
 // from the issuing warps (whose instruction streams are the critical path): 3 = every group three terms, kslab 1
 // (parity); 1 = every group a single term, kslab 2 (fast with the 128 KB ring); 0 = per-group terms at run time
-// (econ, mixed, and fast when the ring is short).
+// (fast when the ring is short, the traced build); 2 = econ (three terms for the first TC_ECON_FIRST_GROUP groups, two
+// after); 5 = mixed (three terms for the first TC_MIXED_FIRST_GROUP groups, one after).
 template <bool TRACE, bool PRED, int UNI>
 __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
-    const int kslab_c = UNI == 3 ? 1 : UNI == 1 ? 2 : P.kslab;
-    auto terms_of = [&](int gi) -> int { return UNI == 3 ? 3 : UNI == 1 ? 1 : (int)P.g[gi].terms; };
+    const int kslab_c = (UNI == 3 || UNI == 2 || UNI == 5) ? 1 : UNI == 1 ? 2 : P.kslab;
+    auto terms_of = [&](int gi) -> int {
+        return UNI == 3 ? 3 : UNI == 1 ? 1 : UNI == 2 ? (gi < TC_ECON_FIRST_GROUP ? 3 : 2)
+                                           : UNI == 5 ? (gi < TC_MIXED_FIRST_GROUP ? 3 : 1) : (int)P.g[gi].terms;
+    };
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
