@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     if (++stage == P.n_stages) stage = 0;
                 }
                 bool pre_waited = false;
-                for (int it = 0; it < nit; ++it) {
+                // One K-step of the group as a lambda so that the common K = 256 case can be unrolled with a compile-time
+                // `it` (accumulate flag, A-chunk barrier map, operand offsets become constants in the issuing warp)
+                auto kstep = [&](const int it) {
                     const int kc = it * kslab;                   // first K=32 slab of this step
                     const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                             }
                             if (++stage == P.n_stages) stage = 0;
                         }
-                        continue;
+                        return;
                     }
                     // ---- 1-term groups (fast / the tail of mixed)
                     if (elect_one_sync()) {
@@ -448,6 +450,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         umma_commit(bar_empty(hi_stage));
                     }
                     __syncwarp();
+                };
+                if (nit == 8) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) kstep(it);
+                } else if (nit == 4) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) kstep(it);
+                } else {
+                    for (int it = 0; it < nit; ++it) kstep(it);
                 }
                 tr.ev(0x700 + gi);                               // group fully issued
                 ++gcount;
