@@ -368,7 +368,9 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     const uint32_t halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 16;   // float4 per pixel
     const uint32_t bias_bytes = (uint32_t)(h->n_bias - h->head_bias0) * 4;                 // head bias only
     const uint32_t ones_bytes = 2 * TC_A_LBO;                                              // constant A operand of the bias slabs
-    const uint32_t fixed = 2 * TC_A_PART_BYTES + bias_bytes + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES + ones_bytes + 16;
+    const uint32_t bslab_bytes = 2 * TC_BSLAB_BYTES;                                        // bias-slab slot + its block of zeros
+    const uint32_t fixed = 2 * TC_A_PART_BYTES + bias_bytes + 320 * 4 + halo_bytes + TC_M * 5 * 4 + TC_BAR_BYTES + ones_bytes +
+                           bslab_bytes + 16;
     int stages = 4;
     while (stages >= 2 && fixed + (uint32_t)stages * TC_STAGE_BYTES > (uint32_t)h->smem_optin) --stages;
     if (stages < 2) return fail(AADFF_E_UNSUPPORTED, "shared memory budget exceeded for this kernel size / channel count");
@@ -381,7 +383,8 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.off_red = P.off_halo + halo_bytes;
     P.off_bar = P.off_red + TC_M * 5 * 4;
     P.off_ones = (P.off_bar + TC_BAR_BYTES + 15u) & ~15u;
-    const uint32_t smem = P.off_ones + ones_bytes;
+    P.off_bslab = P.off_ones + ones_bytes;
+    const uint32_t smem = P.off_bslab + bslab_bytes;
     // no layer needs lo operands (fast mode): the A_lo region doubles the ring to 128 KB, organised as four
     // 32 KB stages (two packed K=32 slabs each) so that every issue iteration queues four MMAs
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;

@@ -52,7 +52,8 @@ constexpr int TC_MAX_GROUPS = 16;
 constexpr int TC_MAX_STAGES = 8;        // 4 in the stage area (+ 4 in the A_lo region when no layer needs lo parts)
 constexpr int TC_MAX_KS = 31;
 constexpr int TC_MAX_C = 4;
-constexpr int TC_BAR_BYTES = 256;        // mbarriers (2*8 + 4 + 2 + 2) * 8 B + TMEM slot
+constexpr int TC_BAR_BYTES = 256;        // mbarriers (2*8 + 8 + 2 + 2 + 2) * 8 B + TMEM slot
+constexpr int TC_BSLAB_BYTES = TC_HID * 16;   // K-group 0 of a bias slab (the only non-zero part): 4 KB
 constexpr int TC_TRACE_N = 4096;         // trace entries per role
 constexpr int TC_MIXED_FIRST_GROUP = 3;  // mixed: groups 0..2 (L1..L3) three terms, one term after
 constexpr int TC_ECON_FIRST_GROUP = 4;   // econ: groups 0..3 (L1..L4) three terms, L5.. and the head two (econ_calib.h)
@@ -82,6 +83,7 @@ struct TcParams {
     long long n_tiles;
     // shared-memory byte offsets
     uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar, off_ones;
+    uint32_t off_bslab;     // bias-slab slot: [256 x 8] halves (K columns 0..7) + a shared [256 x 8] block of zeros (K 8..15)
     uint32_t dbg;           // what-if timing switches (results invalid): 1 = no weight copies, 2 = no A stores
     // pred mode (kernel instantiated with PRED = true): probes [M,4] in, L1-normalised PSFs [M, ks*ks] out
     const float* probes;
@@ -218,8 +220,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     auto bar_aready = [&](int j) { return bar0 + 8u * (2 * TC_MAX_STAGES + j); };
     auto bar_accfull = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 8 + b); };
     auto bar_accfree = [&](int b) { return bar0 + 8u * (2 * TC_MAX_STAGES + 10 + b); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 12));
-    static_assert(8 * (2 * TC_MAX_STAGES + 12) + 4 <= TC_BAR_BYTES, "barrier area too small");
+    auto bar_bfull = [&]() { return bar0 + 8u * (2 * TC_MAX_STAGES + 12); };      // bias-slab slot filled / consumed
+    auto bar_bempty = [&]() { return bar0 + 8u * (2 * TC_MAX_STAGES + 13); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * (2 * TC_MAX_STAGES + 14));
+    static_assert(8 * (2 * TC_MAX_STAGES + 14) + 4 <= TC_BAR_BYTES, "barrier area too small");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
@@ -232,6 +236,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
             // checks at K-steps 0, 1, 2 and 4: every spared wait is ~90 cycles of idle tensor pipe)
             mbar_init(bar_aready(j), (kslab_c == 2 || j < 4) ? TC_EPI_WARPS : 2 * TC_EPI_WARPS);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_accfull(b), 1); mbar_init(bar_accfree(b), TC_EPI_WARPS); }
+        mbar_init(bar_bfull(), 1);
+        mbar_init(bar_bempty(), 1);
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < P.n_bias - P.bias_skip; i += TC_NT) s_bias[i] = __ldg(P.bias + P.bias_skip + i);
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         if (i < TC_M) v.x = 0x3C003C00u;                      // halves (1.0, 1.0) in K columns 0, 1
         *reinterpret_cast<uint4*>(smem + P.off_ones + (i < TC_M ? 0 : TC_A_LBO) + (i % TC_M) * 16) = v;
     }
+    for (int i = threadIdx.x; i < TC_BSLAB_BYTES / 16; i += TC_NT)            // K columns 8..15 of every bias slab: zeros
+        *reinterpret_cast<uint4*>(smem + P.off_bslab + TC_BSLAB_BYTES + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     for (int i = threadIdx.x; i < 320; i += TC_NT) s_w0[i] = __ldg(P.w0b0 + i);
     if (warp == TC_WARP_PRODUCER) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     if (warp == TC_WARP_PRODUCER) {
         // =========================================================== weight producer (converged warp)
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, bphase = 0;
         TcTrace<TRACE> tr; tr.init(lane == 0 ? P.trace : nullptr, 0);
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             for (int gi = 0; gi < P.n_groups; ++gi) {
@@ -262,20 +270,22 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 const uint8_t* src = P.wpack + P.g[gi].w_off;
                 const int kslab = kslab_c;
                 const int nit = P.g[gi].K / (TC_SLAB_K * kslab);
-                if (gi < P.n_hidden) {                           // bias slab: N x 16 halves, one ring stage
-                    const uint32_t bbytes = (uint32_t)P.g[gi].N * 32;
-                    mbar_wait(bar_empty(stage), phase ^ 1);
+                if (gi < P.n_hidden) {
+                    // bias slab: only its K-group 0 (N x 8 halves, 4 KB) is copied, into a dedicated slot (not a ring
+                    // stage: every group then consumes a multiple of four stages and the ring position of a K-step is
+                    // a compile-time constant in the specialised kernels)
+                    mbar_wait(bar_bempty(), bphase ^ 1);
                     if (elect_one_sync()) {
                         if (P.dbg & 1) {
-                            mbar_arrive(bar_full(stage));
+                            mbar_arrive(bar_bfull());
                         } else {
-                            mbar_arrive_expect_tx(bar_full(stage), bbytes);
-                            bulk_g2s(stage_addr(stage), src, bbytes, bar_full(stage));
+                            mbar_arrive_expect_tx(bar_bfull(), TC_BSLAB_BYTES);
+                            bulk_g2s(sbase + P.off_bslab, src, TC_BSLAB_BYTES, bar_bfull());
                         }
                     }
                     __syncwarp();
-                    if (++stage == P.n_stages) { stage = 0; phase ^= 1; }
-                    src += bbytes;
+                    bphase ^= 1;
+                    src += (uint32_t)P.g[gi].N * 32;             // the packed slab also carries its (all-zero) K-group 1
                 }
                 for (int it = 0; it < nit; ++it) {
                     // 3-term groups, 4-stage ring: the hi and the lo slab of a K-slab complete ONE barrier (the hi
@@ -309,6 +319,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         // =========================================================== MMA issuer (converged warp, elected lane)
         int stage = 0;
         uint32_t fbits = 0, aphase = 0, frphase = 0;      // bit s / j / b = parity to wait for next on that barrier
+        uint32_t bphase = 0;                               // bias-slab slot
         uint32_t gcount = 0;
         TcTrace<TRACE> tr; tr.init(lane == 0 ? P.trace : nullptr, 1);
         // descriptors: everything but the 14-bit start-address field (16-byte units) is loop invariant
@@ -344,15 +355,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 if (has_bias) {
                     // accumulator := bias (one MMA, constant A operand): needs no activations, so it is issued before
                     // the first a_ready wait and runs inside the hand-off bubble between two layers
-                    { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }
+                    mbar_wait(bar_bfull(), bphase);
+                    bphase ^= 1;
                     tc_fence_after_sync();
                     if (elect_one_sync()) {
-                        const uint64_t dbb = (db0 & ~0x3FFFull) | ((stage_addr(stage) & 0x3FFFFu) >> 4);
-                        umma_f16_ss(d_tmem, da_ones, dbb, idesc, 0);
-                        umma_commit(bar_empty(stage));
+                        // B = [256 x 16]: K-group 0 in the slot, K-group 1 = the block of zeros behind it (LBO = 4 KB)
+                        umma_f16_ss(d_tmem, da_ones, umma_smem_desc(sbase + P.off_bslab, TC_BSLAB_BYTES, 128), idesc, 0);
+                        umma_commit(bar_bempty());
                     }
                     __syncwarp();
-                    if (++stage == P.n_stages) stage = 0;
                 }
                 bool pre_waited = false;
                 // One K-step of the group as a lambda so that the common K = 256 case can be unrolled with a compile-time
