@@ -298,17 +298,12 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         if (rc) { aadff_psfnet_destroy(h); return rc; }
         const int so = h->smem_optin;
         const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 0>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 1>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 3>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 2>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 2>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 5>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 5>, attr, so));
         CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 0>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 1>, attr, so));
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 3>, attr, so));
+#define AADFF_SET_ATTR(U)                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, U>, attr, so));   \
+        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, U>, attr, so));
+        AADFF_SET_ATTR(0) AADFF_SET_ATTR(1) AADFF_SET_ATTR(3) AADFF_SET_ATTR(13) AADFF_SET_ATTR(12) AADFF_SET_ATTR(15)
+#undef AADFF_SET_ATTR
     }
     *out = h;
     return AADFF_OK;
@@ -390,30 +385,39 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;
     P.n_stages = (P.kslab == 2) ? 4 : stages;
     const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
-    // kernel specialisation: 3 = all groups three-term (parity), 1 = all single-term with the long ring (fast),
-    // 0 = per-group terms (econ, mixed, short-ring fast, and the traced build)
-    bool all3 = true, all1 = true;
-    for (int i = 0; i < h->n_groups; ++i) { all3 &= (P.g[i].terms == 3); all1 &= (P.g[i].terms == 1); }
-    bool econ_pat = (P.kslab == 1);
-    for (int i = 0; i < h->n_groups; ++i) econ_pat &= (P.g[i].terms == (i < TC_ECON_FIRST_GROUP ? 3 : 2));
-    bool mixed_pat = (P.kslab == 1);
-    for (int i = 0; i < h->n_groups; ++i) mixed_pat &= (P.g[i].terms == (i < TC_MIXED_FIRST_GROUP ? 3 : 1));
+    // kernel specialisation (fused_tc_kernel.cuh, template UNI): pattern 3 = all groups three-term (parity), 1 = all
+    // single-term with the long ring (fast), 2 = econ, 5 = mixed, 0 = per-group terms at run time; +10 when the ring has
+    // four stages and every group consumes a multiple of four of them (ring position of a K-step = compile-time)
+    bool all3 = true, all1 = true, econ_pat = true, mixed_pat = true, aligned = (P.n_stages == 4 && P.kslab == 1);
+    for (int i = 0; i < h->n_groups; ++i) {
+        const int t = P.g[i].terms;
+        all3 &= (t == 3);
+        all1 &= (t == 1);
+        econ_pat &= (t == (i < TC_ECON_FIRST_GROUP ? 3 : 2));
+        mixed_pat &= (t == (i < TC_MIXED_FIRST_GROUP ? 3 : 1));
+        aligned &= (((P.g[i].K / TC_SLAB_K) * (t == 3 ? 2 : 1)) % 4 == 0);
+    }
     static_assert(TC_ECON_FIRST_GROUP == TC_ECON_FIRST_LAYER - 1, "group g holds layer g + 1");
-    const int uni = (all3 && P.kslab == 1) ? 3 : (all1 && P.kslab == 2) ? 1 : econ_pat ? 2 : mixed_pat ? 5 : 0;
-    if (P.trace != nullptr && P.probes == nullptr)
+    int uni = 0;
+    if (all3 && P.kslab == 1) uni = aligned ? 13 : 3;
+    else if (all1 && P.kslab == 2) uni = 1;
+    else if (econ_pat && aligned) uni = 12;
+    else if (mixed_pat && aligned) uni = 15;
+    if (P.trace != nullptr && P.probes == nullptr) {
         fused_psfnet_render_kernel<true, false, 0><<<grid, TC_NT, smem, st>>>(P);
-    else if (P.probes != nullptr) {
-        if (uni == 3) fused_psfnet_render_kernel<false, true, 3><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 2) fused_psfnet_render_kernel<false, true, 2><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 5) fused_psfnet_render_kernel<false, true, 5><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 1) fused_psfnet_render_kernel<false, true, 1><<<grid, TC_NT, smem, st>>>(P);
-        else fused_psfnet_render_kernel<false, true, 0><<<grid, TC_NT, smem, st>>>(P);
     } else {
-        if (uni == 3) fused_psfnet_render_kernel<false, false, 3><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 2) fused_psfnet_render_kernel<false, false, 2><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 5) fused_psfnet_render_kernel<false, false, 5><<<grid, TC_NT, smem, st>>>(P);
-        else if (uni == 1) fused_psfnet_render_kernel<false, false, 1><<<grid, TC_NT, smem, st>>>(P);
-        else fused_psfnet_render_kernel<false, false, 0><<<grid, TC_NT, smem, st>>>(P);
+#define AADFF_LAUNCH(U)                                                                                   \
+        case U:                                                                                           \
+            if (P.probes != nullptr) fused_psfnet_render_kernel<false, true, U><<<grid, TC_NT, smem, st>>>(P);   \
+            else fused_psfnet_render_kernel<false, false, U><<<grid, TC_NT, smem, st>>>(P);               \
+            break;
+        switch (uni) {
+            AADFF_LAUNCH(1) AADFF_LAUNCH(3) AADFF_LAUNCH(13) AADFF_LAUNCH(12) AADFF_LAUNCH(15)
+            default:
+                if (P.probes != nullptr) fused_psfnet_render_kernel<false, true, 0><<<grid, TC_NT, smem, st>>>(P);
+                else fused_psfnet_render_kernel<false, false, 0><<<grid, TC_NT, smem, st>>>(P);
+        }
+#undef AADFF_LAUNCH
     }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());

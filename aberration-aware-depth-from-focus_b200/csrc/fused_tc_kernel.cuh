@@ -187,16 +187,19 @@ constexpr int TC_WARP_PRODUCER = TC_EPI_WARPS;       // warp 8
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + 1;        // warp 9
 
 // UNI specialises the kernel on the arithmetic of the whole network so that the mode-dependent branches disappear
-// from the issuing warps (whose instruction streams are the critical path): 3 = every group three terms, kslab 1
-// (parity); 1 = every group a single term, kslab 2 (fast with the 128 KB ring); 0 = per-group terms at run time
-// (fast when the ring is short, the traced build); 2 = econ (three terms for the first TC_ECON_FIRST_GROUP groups, two
-// after); 5 = mixed (three terms for the first TC_MIXED_FIRST_GROUP groups, one after).
+// from the issuing warps (whose instruction streams are the critical path).  UNI % 10 = pattern: 3 = every group three
+// terms, kslab 1 (parity); 1 = every group a single term, kslab 2 (fast with the 128 KB ring); 2 = econ (three terms for
+// the first TC_ECON_FIRST_GROUP groups, two after); 5 = mixed (three terms for the first TC_MIXED_FIRST_GROUP groups,
+// one after); 0 = per-group terms at run time (short rings, the traced build).  UNI >= 10 ("aligned"): the ring has four
+// stages and every group consumes a multiple of four, so the ring stage of a K-step is a compile-time constant too.
 template <bool TRACE, bool PRED, int UNI>
 __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __grid_constant__ TcParams P) {
-    const int kslab_c = (UNI == 3 || UNI == 2 || UNI == 5) ? 1 : UNI == 1 ? 2 : P.kslab;
+    constexpr int UM = UNI % 10;
+    constexpr bool ALIGNED = UNI >= 10;
+    const int kslab_c = (UM == 3 || UM == 2 || UM == 5) ? 1 : UM == 1 ? 2 : P.kslab;
     auto terms_of = [&](int gi) -> int {
-        return UNI == 3 ? 3 : UNI == 1 ? 1 : UNI == 2 ? (gi < TC_ECON_FIRST_GROUP ? 3 : 2)
-                                           : UNI == 5 ? (gi < TC_MIXED_FIRST_GROUP ? 3 : 1) : (int)P.g[gi].terms;
+        return UM == 3 ? 3 : UM == 1 ? 1 : UM == 2 ? (gi < TC_ECON_FIRST_GROUP ? 3 : 2)
+                                         : UM == 5 ? (gi < TC_MIXED_FIRST_GROUP ? 3 : 1) : (int)P.g[gi].terms;
     };
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     const int kc = it * kslab;                   // first K=32 slab of this step
                     const uint64_t ah = da_hi + (uint32_t)kc * (2 * KSTEP_A);
                     const uint64_t al = da_lo + (uint32_t)kc * (2 * KSTEP_A);
+                    if (ALIGNED) stage = (three ? 2 * it : it) & 3;   // groups start at ring position 0 (host-checked)
                     if (!pre_waited) {
                         tr.ev(0x500 + kc);
                         { mbar_wait(bar_full(stage), (fbits >> stage) & 1); fbits ^= 1u << stage; }      // hi weight stage (prefetched long ago)
@@ -386,11 +390,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     tc_fence_after_sync();
                     const int hi_stage = stage;
                     const bool last = (it + 1 == nit);
+                    auto next_stage = [&](int st) { return ALIGNED ? ((st + 1) & 3) : (st + 1 == P.n_stages ? 0 : st + 1); };
                     if (use_al) {
                         // ---- 2-/3-term groups (kslab == 1): ONE elected block per K-slab -- every extra elect / syncwarp /
                         //      barrier probe in this warp delays the next MMA (its instruction stream is the critical path)
-                        if (++stage == P.n_stages) stage = 0;
-                        const bool merged = three && P.n_stages >= 4;       // lo bytes arrived with the pair barrier
+                        stage = next_stage(stage);
+                        const bool merged = three && (ALIGNED || P.n_stages >= 4);       // lo bytes arrived with the pair barrier
                         if (elect_one_sync()) {
                             const uint64_t db = (db0 & ~0x3FFFull) | ((stage_addr(hi_stage) & 0x3FFFFu) >> 4);
                             umma_f16_ss(d_tmem, ah, db, idesc, has_bias || it != 0);
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                                 }
                                 __syncwarp();
                             }
-                            if (++stage == P.n_stages) stage = 0;
+                            stage = next_stage(stage);
                         }
                         return;
                     }
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                         }
                     }
                     __syncwarp();
-                    if (++stage == P.n_stages) stage = 0;
+                    stage = next_stage(stage);
                     // ---- waits of the next step, while the MMAs above execute (before the commit that drains the pipe)
                     pre_waited = false;
                     if (it + 1 < nit) {
