@@ -70,7 +70,7 @@ def executed_mma_flops_per_pixel(ks, mode):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` captures
 # (profiles/r01_ncu_summary.md); the 15.7 MB output of c2 was still L2-resident when the capture ended.
-NCU_TRAFFIC_BYTES = {("c2", "parity"): 6.65e6, ("c2", "fast"): 5.50e6}
+NCU_TRAFFIC_BYTES = {("c2", "parity"): 6.61e6, ("c2", "fast"): 5.45e6}
 
 
 def weights_for(ks):
