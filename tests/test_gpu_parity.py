@@ -110,6 +110,32 @@ def test_gather_every_kernel_size_vs_oracle(pkg, ks):
         assert maxabs(old, ref) < 2e-6, (ks, N, C, H, W)
 
 
+@pytest.mark.parametrize("hidden_layers", [0, 2, 5])
+def test_other_network_depths_vs_oracle(pkg, hidden_layers):
+    """The C ABI takes any number of 256-wide hidden layers: shallower / deeper MLPs than the reference's
+    MLP(4, k^2, 256, 8) exercise the other group counts of the kernel specialisations (all-three-term, econ and mixed
+    patterns with fewer groups, the ring alignment check) against the CPU oracle."""
+    from deeplens.psfnet_arch import MLP
+    ks = 11
+    l = pkg.PSFNet(kernel_size=ks, device="cuda")
+    torch.manual_seed(40 + hidden_layers)
+    l.psfnet = MLP(in_features=4, out_features=ks * ks, hidden_features=256, hidden_layers=hidden_layers).to("cuda")
+    l.psfnet._evaluator = l._mlp_eval
+    l._native = None
+    gen = torch.Generator().manual_seed(7 + hidden_layers)
+    with torch.no_grad():
+        for lin in l.psfnet.linear_layers():
+            lin.bias.copy_(((torch.rand(lin.bias.shape, generator=gen) - 0.5) * 0.2).cuda())
+    Ws = [lin.weight.detach().cpu() for lin in l.psfnet.linear_layers()]
+    bs = [lin.bias.detach().cpu() for lin in l.psfnet.linear_layers()]
+    img, dm = orc.synthetic_rgbd(2, 24, 40, seed=3)
+    foc = -orc.synthetic_focus(dm, 3) * 1e3
+    ref = orc.render_stack(Ws, bs, img, -dm * 1e3, foc, ks)
+    for mode in ("parity", "fp32", "fast", "econ", "mixed"):
+        out = l.render_stack(img.cuda(), -dm.cuda() * 1e3, foc.cuda(), mode=mode)
+        assert maxabs(out, ref) < (1e-4 if mode == "econ" else TOL[mode]), (hidden_layers, mode)
+
+
 def test_pred_golden(lens):
     g = load_golden("kat_a_pred.npz")
     psf = lens.pred(T(g["inp"]).cuda())
