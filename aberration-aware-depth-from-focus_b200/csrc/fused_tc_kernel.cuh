@@ -859,7 +859,7 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *slot;
-    uint32_t done_phase = 0;
+    uint32_t done_phase = 0, cph = 0;
     for (int p = 0; p < n_patterns; ++p) {
         const int m = mmas_per_commit[p];
         if (threadIdx.x == 0) *stop = 0;
@@ -885,9 +885,9 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
             const long long t2 = clock64();
             if (lane == 0) { out[p * 2] = t1 - t0; out[p * 2 + 1] = t2 - t0; *stop = 1; }
         } else if (warp == 1 && do_copy) {
-            // 16 KB copies into the upper 48 KB of the B region, three in flight
+            // 16 KB copies into the upper 48 KB of the B region, three in flight; `cph` (one parity bit per barrier)
+            // lives across patterns, and every copy is waited for before the pattern ends
             unsigned long long n = 0;
-            uint32_t ph = 0;
             if (lane == 0) {
                 for (int i = 0; i < 3; ++i) {
                     mbar_arrive_expect_tx(bar_copy + 8 * i, 16384);
@@ -895,14 +895,17 @@ debug_mma_timing_kernel(unsigned long long* out, int n_patterns, const int* mmas
                 }
                 while (!*stop) {
                     for (int i = 0; i < 3; ++i) {
-                        mbar_wait(bar_copy + 8 * i, ph);
+                        mbar_wait(bar_copy + 8 * i, (cph >> i) & 1);
+                        cph ^= 1u << i;
                         mbar_arrive_expect_tx(bar_copy + 8 * i, 16384);
                         bulk_g2s(b_sm + 16384 + 16384 * i, gsrc + 16384 * i, 16384, bar_copy + 8 * i);
                         ++n;
                     }
-                    ph ^= 1;
                 }
-                for (int i = 0; i < 3; ++i) mbar_wait(bar_copy + 8 * i, ph);
+                for (int i = 0; i < 3; ++i) {
+                    mbar_wait(bar_copy + 8 * i, (cph >> i) & 1);
+                    cph ^= 1u << i;
+                }
                 out[32 + p] = n * 16384ull;
             }
             __syncwarp();

@@ -259,7 +259,7 @@ def stage_mma_timing():
     reps = 16
     # epi_load: low 16 bits = competing TMEM reads, bit 16 = bulk copies into smem, bit 17 = st.shared stream
     for N in (256, 128):
-        for epi in (0, 4000, 1 << 16, 1 << 17):
+        for epi in (0, 4000, 1 << 16, 1 << 17, 3 << 16):
             out = np.zeros(64, dtype=np.uint64)
             nat.check(nat.lib.aadff_debug_mma_timing(ctypes.c_void_p(pats.ctypes.data), len(pats), reps, N, epi,
                                                      ctypes.c_void_p(out.ctypes.data), 0))
