@@ -10,9 +10,10 @@
 // TMEM lane per pixel.  A persistent CTA (one per SM) walks tiles round-robin.
 //
 //   warps 0-7   epilogue/compute (256 threads, two warps per TMEM lane quadrant):
-//               layer 0 (4->64) in fp32 FFMA, per-layer epilogue (TMEM -> +bias -> ReLU ->
-//               fp16 hi/lo split -> K-major smem operand for the next layer), and the head
-//               epilogue (sigmoid -> k x k gather from the smem halo tile -> normalise -> store)
+//               layer 0 (4->64) in fp32 FFMA, per-layer epilogue (TMEM -> ReLU + fp16 hi/lo split in
+//               the conversions -> K-major smem operand for the next layer; the hidden-layer bias is
+//               put into the accumulator by a K=16 "bias slab" MMA), and the head epilogue
+//               (sigmoid -> k x k gather from the smem halo tile -> normalise -> store)
 //   warp 8      weight producer: streams pre-packed fp16 weight slabs L2 -> smem ring
 //               (cp.async.bulk + mbarrier complete_tx), also owns TMEM alloc/dealloc
 //   warp 9      MMA issuer: converged warp, an elected lane issues tcgen05.mma (kind::f16,
@@ -23,7 +24,8 @@
 // (SURVEY.md 7.3), so in parity mode every product is evaluated as
 //   A*W ~= Ah*Wh + Al*Wh + Ah*Wl   (Ah = fp16(A), Al = fp16(A - Ah), same for W)
 // with fp32 accumulation in TMEM: three tcgen05.mma per K-step.  "terms" is per layer, so
-// fast (1-term) and mixed modes are the same kernel.
+// fast (1-term), econ and mixed modes are the same kernel source; the template parameter UNI
+// compiles one variant per arithmetic pattern (see the kernel's comment).
 //
 // Intra-tile pipelining: the epilogue of layer l hands its output to the MMA warp in 32/64-column
 // chunks (a_ready[j]); the MMAs of layer l+1 for K-chunk j start as soon as chunk j is in smem and
