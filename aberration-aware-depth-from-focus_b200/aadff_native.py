@@ -73,6 +73,13 @@ def _load() -> ctypes.CDLL:
     lib.aadff_render_stack_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 5 + \
                                           [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    lib.aadff_render_stack_rows_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 5 + \
+                                               [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int64,
+                                                ctypes.c_int64, ctypes.c_void_p]
+    lib.aadff_tile_row_height.restype = ctypes.c_int
+    lib.aadff_econ_first_group.restype = ctypes.c_int
+    lib.aadff_any_negative_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     lib.aadff_render_stack_host_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 5 + \
                                                [ctypes.c_float, ctypes.c_float, ctypes.c_int]
     lib.aadff_psfnet_pred_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
@@ -82,14 +89,15 @@ def _load() -> ctypes.CDLL:
     lib.aadff_local_psf_render_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     lib.aadff_debug_umma_gemm.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3
     lib.aadff_thinlens_render_f32.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_float] * 5 + \
-                                             [ctypes.c_int, ctypes.c_void_p]
+                                             [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     lib.aadff_debug_set_desc_swap.argtypes = [ctypes.c_int]
     lib.aadff_debug_econ_round.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p]
     lib.aadff_debug_econ_round.restype = ctypes.c_int
     lib.aadff_select_focus_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]
-    for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32",
+    for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32", "aadff_render_stack_rows_f32",
+               "aadff_any_negative_f32",
                "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_psfnet_pred_tc_f32", "aadff_local_psf_render_f32", "aadff_thinlens_render_f32", "aadff_select_focus_f32",
                "aadff_debug_umma_gemm", "aadff_debug_set_desc_swap"):
         getattr(lib, fn).restype = ctypes.c_int
@@ -106,6 +114,11 @@ class AadffError(RuntimeError):
 def check(rc: int) -> None:
     if rc != 0:
         raise AadffError(f"libaadff error {rc}: {lib.aadff_last_error().decode()}")
+
+
+def econ_first_group() -> int:
+    """First tensor-core group (0 = L1) that AADFF_MODE_ECON runs with two MMA terms instead of three."""
+    return int(lib.aadff_econ_first_group())
 
 
 def exported_symbols():

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,11 +40,8 @@ template <int KS, int CN>
 void launch_gc(int grid, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
                int c0) {
     constexpr int smem = GatherCfg<KS>::SMEM_FLOATS(CN) * (int)sizeof(float);      // <= 69.6 KB (ks = 31, 3 channels)
-    if (smem > 48 * 1024) {
-        static std::atomic<bool> attr_set{false};              // one flag per instantiation
-        if (!attr_set.exchange(true))
-            cudaFuncSetAttribute(local_psf_coalesced_kernel<KS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    }
+    if (smem > 48 * 1024)      // the attribute is per device: set it on every launch (a host-side table write)
+        cudaFuncSetAttribute(local_psf_coalesced_kernel<KS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     local_psf_coalesced_kernel<KS, CN><<<grid, GC_WARPS * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
 }
 template <int KS>
@@ -139,7 +137,15 @@ struct aadff_psfnet {
     float* d_bias_tc = nullptr;
     float* d_w0b0 = nullptr;
     TcGroup groups[TC_MAX_GROUPS]{};
-    uint32_t w_off_econ[TC_MAX_GROUPS]{};   // econ mode, 2-term groups: calibrated fp16 weights (econ_calib.h)
+    // econ mode, 2-term groups: calibrated fp16 weights (econ_calib.h), built on the first AADFF_MODE_ECON launch
+    // (the calibration is a host pass of a few hundred ms that parity / fast / fp32 users should not pay for)
+    uint32_t w_off_econ[TC_MAX_GROUPS]{};
+    uint8_t* d_wpack_econ = nullptr;        // main pack followed by the calibrated slabs
+    size_t pack_bytes = 0;
+    bool econ_ready = false;
+    std::mutex econ_mu;
+    std::vector<std::vector<float>> host_w, host_b;   // fp32 copy of the state_dict (calibration input)
+    std::vector<int> host_dims;
     int n_groups = 0, n_hidden = 0, n_bias = 0, head_bias0 = 0;
     // host-call workspace
     cudaStream_t ws_stream = nullptr, ws_copy_stream = nullptr;
@@ -218,8 +224,16 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         h->f32.k[l] = K;
         h->f32.npad[l] = npad;
     }
-    CUDA_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
+#define CREATE_TRY(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            aadff_psfnet_destroy(h);                                                             \
+            return fail(AADFF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+        }                                                                                        \
+    } while (0)
+    CREATE_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
+    CREATE_TRY(cudaFuncSetAttribute(mlp_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F32_SMEM));
 
     // ---- tcgen05 path: needs the PSFNet architecture 4 -> 64 -> 256 -> 256 x n -> ks^2
     h->tc_ok = true;
@@ -268,23 +282,13 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         }
         h->n_groups = gi;
         h->n_bias = (int)bias_tc.size();
-        // econ mode: L5.. and the head run 2 terms (Ah*Wh + Al*Wh) on output-error-calibrated fp16 weights
-        {
-            std::vector<std::vector<float>> wq;
-            calibrate_econ(weights, biases, dims, n_layers, TC_ECON_FIRST_LAYER, wq);
-            for (int g2 = 0; g2 < h->n_groups; ++g2) {
-                const bool hidden = g2 < h->n_hidden;
-                const int l = hidden ? g2 + 1 : L;
-                h->w_off_econ[g2] = h->groups[g2].w_off;                  // plain rounding unless calibrated
-                if (l < TC_ECON_FIRST_LAYER || wq[l].empty()) continue;
-                h->w_off_econ[g2] = (uint32_t)(pack.size() * sizeof(__half));
-                if (hidden) {
-                    pack_bias_slab(biases[l], TC_HID, pack);
-                    pack_group(wq[l].data(), dims[l + 1], dims[l], 0, TC_HID, pack);
-                }
-                else pack_group(wq[l].data(), h->kk, TC_HID, h->groups[g2].tap0, h->groups[g2].N, pack);
-            }
+        // econ mode needs the fp32 weights again (lazy calibration, ensure_econ below)
+        h->host_dims.assign(dims, dims + n_layers + 1);
+        for (int l = 0; l < n_layers; ++l) {
+            h->host_w.emplace_back(weights[l], weights[l] + (size_t)dims[l] * dims[l + 1]);
+            h->host_b.emplace_back(biases[l], biases[l] + dims[l + 1]);
         }
+        h->pack_bytes = pack.size() * sizeof(__half);
         std::vector<float> w0b0(320);
         std::memcpy(w0b0.data(), weights[0], 256 * sizeof(float));
         std::memcpy(w0b0.data() + 256, biases[0], 64 * sizeof(float));
@@ -298,13 +302,14 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         if (rc) { aadff_psfnet_destroy(h); return rc; }
         const int so = h->smem_optin;
         const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
 #define AADFF_SET_ATTR(U)                                                                        \
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, U>, attr, so));   \
-        CUDA_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, U>, attr, so));
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, U>, attr, so));   \
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, U>, attr, so));
         AADFF_SET_ATTR(0) AADFF_SET_ATTR(1) AADFF_SET_ATTR(3) AADFF_SET_ATTR(13) AADFF_SET_ATTR(12) AADFF_SET_ATTR(15)
 #undef AADFF_SET_ATTR
     }
+#undef CREATE_TRY
     *out = h;
     return AADFF_OK;
 }
@@ -314,6 +319,7 @@ int aadff_psfnet_destroy(aadff_psfnet_t h) {
     DeviceGuard guard(h->device);
     for (float* p : h->owned) cudaFree(p);
     cudaFree(h->d_wpack);
+    cudaFree(h->d_wpack_econ);
     cudaFree(h->d_bias_tc);
     cudaFree(h->d_w0b0);
     cudaFree(h->ws);
@@ -324,12 +330,54 @@ int aadff_psfnet_destroy(aadff_psfnet_t h) {
     return AADFF_OK;
 }
 
-static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st, const float* probes = nullptr,
-                     float* psf_out = nullptr, long long n_probes = 0) {
+// First AADFF_MODE_ECON launch on a handle: calibrate the fp16 rounding of the 2-term layers on the host
+// (econ_calib.h), pack them and place them behind a copy of the main pack.  Synchronous, once per handle.
+static int ensure_econ(aadff_psfnet_t h) {
+    std::lock_guard<std::mutex> lock(h->econ_mu);
+    if (h->econ_ready) return AADFF_OK;
+    const int n_layers = h->n_layers, L = n_layers - 1;
+    std::vector<const float*> W(n_layers), B(n_layers);
+    for (int l = 0; l < n_layers; ++l) { W[l] = h->host_w[l].data(); B[l] = h->host_b[l].data(); }
+    std::vector<std::vector<float>> wq;
+    calibrate_econ(W.data(), B.data(), h->host_dims.data(), n_layers, TC_ECON_FIRST_LAYER, wq);
+    std::vector<__half> pack;
+    for (int g2 = 0; g2 < h->n_groups; ++g2) {
+        const bool hidden = g2 < h->n_hidden;
+        const int l = hidden ? g2 + 1 : L;
+        h->w_off_econ[g2] = h->groups[g2].w_off;                  // plain rounding unless calibrated
+        if (l < TC_ECON_FIRST_LAYER || wq[l].empty()) continue;
+        h->w_off_econ[g2] = (uint32_t)(h->pack_bytes + pack.size() * sizeof(__half));
+        if (hidden) {
+            pack_bias_slab(B[l], TC_HID, pack);
+            pack_group(wq[l].data(), h->host_dims[l + 1], h->host_dims[l], 0, TC_HID, pack);
+        } else {
+            pack_group(wq[l].data(), h->kk, TC_HID, h->groups[g2].tap0, h->groups[g2].N, pack);
+        }
+    }
+    uint8_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d), h->pack_bytes + pack.size() * sizeof(__half)));
+    cudaError_t e = cudaMemcpy(d, h->d_wpack, h->pack_bytes, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + h->pack_bytes, pack.data(), pack.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(AADFF_E_CUDA, std::string("econ weight upload: ") + cudaGetErrorString(e));
+    }
+    h->d_wpack_econ = d;
+    h->econ_ready = true;
+    return AADFF_OK;
+}
+
+static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st, long long tile_row0 = 0,
+                     long long tile_row1 = -1, const float* probes = nullptr, float* psf_out = nullptr,
+                     long long n_probes = 0) {
     if (!h->tc_ok) return fail(AADFF_E_UNSUPPORTED, "tensor-core path unavailable: " + h->tc_why + " (use AADFF_MODE_FP32)");
+    if (mode == AADFF_MODE_ECON) {
+        const int rc = ensure_econ(h);
+        if (rc) return rc;
+    }
     TcParams P{};
     P.ra = ra;
-    P.wpack = h->d_wpack;
+    P.wpack = (mode == AADFF_MODE_ECON) ? h->d_wpack_econ : h->d_wpack;
     P.bias = h->d_bias_tc;
     P.w0b0 = h->d_w0b0;
     P.n_groups = h->n_groups;
@@ -351,6 +399,11 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
     P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
     P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
+    if (tile_row1 >= 0) {                                      // a contiguous run of tile rows of the flattened stack
+        P.tile0 = tile_row0 * P.tiles_x;
+        P.n_tiles = (tile_row1 - tile_row0) * P.tiles_x;
+        if (P.n_tiles <= 0) return AADFF_OK;
+    }
     if (probes != nullptr) {                                   // pred mode: 128 probes per tile, no image
         P.probes = probes;
         P.psf_out = psf_out;
@@ -426,7 +479,20 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
 
 static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, int foc_stride,
                              float* out, const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
-                             float d_max, int mode, void* stream);
+                             float d_max, int mode, void* stream, long long tile_row0 = 0, long long tile_row1 = -1);
+
+int aadff_tile_row_height(void) { return TC_TILE_H; }
+int aadff_econ_first_group(void) { return TC_ECON_FIRST_GROUP; }
+
+int aadff_render_stack_rows_f32(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, float* out,
+                                const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                                float d_max, int mode, int64_t tile_row_begin, int64_t tile_row_end, void* stream) {
+    const long long total = (long long)N * S * ((H + TC_TILE_H - 1) / TC_TILE_H);
+    if (tile_row_begin < 0 || tile_row_end < tile_row_begin || tile_row_end > total)
+        return fail(AADFF_E_INVALID, "tile-row range outside [0, N*S*ceil(H/8)]");
+    return render_stack_impl(h, img, depth, foc, S, out, out_strides, N, C, S, H, W, d_min, d_max, mode, stream,
+                             tile_row_begin, tile_row_end);
+}
 
 int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, float* out,
                            const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
@@ -436,7 +502,7 @@ int aadff_render_stack_f32(aadff_psfnet_t h, const float* img, const float* dept
 
 static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* depth, const float* foc, int foc_stride,
                              float* out, const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
-                             float d_max, int mode, void* stream) {
+                             float d_max, int mode, void* stream, long long tile_row0, long long tile_row1) {
     if (!h || !img || !depth || !foc || !out || !out_strides) return fail(AADFF_E_INVALID, "null argument");
     if (N < 0 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
     if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
@@ -459,13 +525,21 @@ static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* de
         ra.c0 = c0;
         ra.C = std::min(4, C - c0);
         if (mode == AADFF_MODE_FP32) {
-            const long long M = (long long)N * S * H * W;
-            const int grid = (int)std::min<long long>((M + F32_TP - 1) / F32_TP, (long long)h->num_sms * 8);
-            mlp_fp32_kernel<true><<<grid, F32_NT, F32_SMEM, st>>>(h->f32, ra, nullptr, nullptr, M);
-            g_launches.fetch_add(1);
-            CUDA_TRY(cudaGetLastError());
+            long long M0 = 0, M = (long long)N * S * H * W;
+            if (tile_row1 >= 0) {                    // tile row R = (image*S + slice)*tiles_y + ty  ->  flat pixel rows
+                const long long tiles_y = (H + TC_TILE_H - 1) / TC_TILE_H;
+                auto flat_row = [&](long long R) { return (R / tiles_y) * H + std::min<long long>((R % tiles_y) * TC_TILE_H, H); };
+                M0 = flat_row(tile_row0) * W;
+                M = flat_row(tile_row1) * W;
+            }
+            if (M > M0) {
+                const int grid = (int)std::min<long long>((M - M0 + F32_TP - 1) / F32_TP, (long long)h->num_sms * 8);
+                mlp_fp32_kernel<true><<<grid, F32_NT, F32_SMEM, st>>>(h->f32, ra, nullptr, nullptr, M0, M);
+                g_launches.fetch_add(1);
+                CUDA_TRY(cudaGetLastError());
+            }
         } else {
-            int rc = launch_tc(h, ra, mode, st);
+            int rc = launch_tc(h, ra, mode, st, tile_row0, tile_row1);
             if (rc) return rc;
         }
     }
@@ -535,7 +609,7 @@ int aadff_psfnet_pred_f32(aadff_psfnet_t h, const float* inp, float* psf, int64_
     RenderArgs ra{};
     ra.ks = h->ks;
     const int grid = (int)std::min<long long>((M + F32_TP - 1) / F32_TP, (long long)h->num_sms * 8);
-    mlp_fp32_kernel<false><<<grid, F32_NT, F32_SMEM, static_cast<cudaStream_t>(stream)>>>(h->f32, ra, inp, psf, M);
+    mlp_fp32_kernel<false><<<grid, F32_NT, F32_SMEM, static_cast<cudaStream_t>(stream)>>>(h->f32, ra, inp, psf, 0, M);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
@@ -552,7 +626,7 @@ int aadff_psfnet_pred_tc_f32(aadff_psfnet_t h, const float* inp, float* psf, int
     if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
     RenderArgs ra{};
     ra.ks = h->ks; ra.N = 1; ra.S = 1; ra.H = 1; ra.W = 1; ra.C = 1; ra.Ctot = 1;
-    return launch_tc(h, ra, mode, static_cast<cudaStream_t>(stream), inp, psf, (long long)M);
+    return launch_tc(h, ra, mode, static_cast<cudaStream_t>(stream), 0, -1, inp, psf, (long long)M);
 }
 
 int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, int N, int C, int H, int W, int ks,
@@ -594,16 +668,13 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
         const int buf_bytes = (P * kk * 4 + 127) / 128 * 128;
         const int HH = nw + ks - 1, pitch = (GS_TILE_W + ks - 1) | 1;
         const int smem = nw * nbuf * buf_bytes + GS_MAXC * HH * pitch * 4 + 16 * nw;
-        static std::atomic<int> attr_smem8{0}, attr_smem6{0};
-        std::atomic<int>& attr = (nw == GS_TILE_H_1BUF) ? attr_smem8 : attr_smem6;
-        if (attr.load() < smem) {
+        if (smem > 48 * 1024) {    // per-device attribute: set on every launch that needs the opt-in
             if (nw == GS_TILE_H_1BUF)
                 CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel<GS_TILE_H_1BUF>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             else
                 CUDA_TRY(cudaFuncSetAttribute(local_psf_stream_kernel<GS_TILE_H_2BUF>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr.store(smem);
         }
         const long long tiles = (long long)N * ((H + nw - 1) / nw) * ((W + GS_TILE_W - 1) / GS_TILE_W);
         const int grid = (int)std::min<long long>(tiles, sms);
@@ -620,9 +691,8 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
         }
         return AADFF_OK;
     }
-    static std::atomic<bool> attr_set{false};
     const int smem = GATHER_WARPS * 32 * (GATHER_TT + 1) * (int)sizeof(float);
-    if (!attr_set.exchange(true))
+    if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(local_psf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long items = (long long)N * H * ((W + 31) / 32);
     const int grid = (int)std::min<long long>((items + GATHER_WARPS - 1) / GATHER_WARPS, (long long)sms * 3);
@@ -635,9 +705,21 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     return AADFF_OK;
 }
 
+int aadff_any_negative_f32(const float* x, int64_t n, unsigned char* flag_dev, void* stream) {
+    if (!x || !flag_dev || n < 0) return fail(AADFF_E_INVALID, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(flag_dev, 0, 1, st));
+    if (n == 0) return AADFF_OK;
+    const int grid = (int)std::min<long long>((n + 255) / 256, 592);
+    any_negative_kernel<<<grid, 256, 0, st>>>(x, (long long)n, flag_dev);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
 int aadff_thinlens_render_f32(const float* img, const float* depth, const float* foc, float* out, int N, int C, int H,
                               int W, int ks, float foc_len, float fnum, float pixel_size, float d_lo, float d_hi,
-                              int flip_sign, void* stream) {
+                              int flip_sign, const unsigned char* flip_sign_dev, void* stream) {
     if (!img || !depth || !foc || !out) return fail(AADFF_E_INVALID, "null argument");
     if (N < 0 || C < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
     if (ks < 1 || (ks % 2) == 0) return fail(AADFF_E_INVALID, "kernel size must be odd and positive");
@@ -652,14 +734,12 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
     a.N = N; a.C = C; a.H = H; a.W = W; a.ks = ks;
     a.k1 = (float)((double)foc_len / (double)fnum);
     a.foc_len = foc_len; a.ps = pixel_size; a.d_lo = d_lo; a.d_hi = d_hi; a.flip = flip_sign ? 1 : 0;
+    a.flip_dev = flip_sign_dev;
     const int HH = TL_TILE_H + ks - 1, pitch = (TL_TILE_W + ks - 1) | 1;
     const int smem = TL_MAXC * HH * pitch * 4;
     if (smem > optin) return fail(AADFF_E_UNSUPPORTED, "kernel size too large for the shared-memory halo tile");
-    static std::atomic<int> attr_smem{0};
-    if (attr_smem.load() < smem) {
+    if (smem > 48 * 1024)      // per-device attribute
         CUDA_TRY(cudaFuncSetAttribute(thinlens_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem.store(smem);
-    }
     const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + TL_TILE_W - 1) / TL_TILE_W);
     const int grid = (int)std::min<long long>(tiles, (long long)sms * 4);
     for (int c0 = 0; c0 < C; c0 += TL_MAXC) {

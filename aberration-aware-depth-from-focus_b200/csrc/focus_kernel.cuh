@@ -35,9 +35,14 @@ select_focus_kernel(const float* __restrict__ depth, long long hw, int num, floa
             vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
         // reference arithmetic order: depth_min + (i * (depth_max - depth_min)) / (num - 1)
+        // An image without a single valid (> 0) depth: the reference raises (torch.min of an empty selection,
+        // dff/utils.py:22) and its training loop skips such batches (2_aber_aware_dff_aif.py:103-105).  Here every
+        // focus distance of that image is a quiet NaN -- an explicit sentinel the caller can test without a sync.
+        const bool none_valid = !(vmin < __int_as_float(0x7f800000));
         const float span = vmax - vmin;
         for (int i = threadIdx.x; i < num; i += 32)
-            out[(long long)blockIdx.x * num + i] = vmin + __fdiv_rn((float)i * span, (float)(num - 1));
+            out[(long long)blockIdx.x * num + i] =
+                none_valid ? __int_as_float(0x7fc00000) : vmin + __fdiv_rn((float)i * span, (float)(num - 1));
     }
 }
 

@@ -82,7 +82,9 @@ struct TcParams {
                             // by the tensor core (first slab of every hidden group = a K=16 "bias slab", see below)
     int kslab;              // packed K=32 slabs per ring stage: 1 (any 3-term layer) or 2 (fast mode, 32 KB stages)
     int tiles_x, tiles_y;
-    long long n_tiles;
+    long long n_tiles;      // tiles of this launch ...
+    long long tile0;        // ... starting at this index of the flattened (image, slice, tile row, tile column) list:
+                            // a launch may cover any contiguous run of tile rows (multi-GPU partition, sharding.py)
     // shared-memory byte offsets
     uint32_t off_stage, off_bias, off_w0, off_halo, off_red, off_bar, off_ones;
     uint32_t off_bslab;     // bias-slab slot: [256 x 8] halves (K columns 0..7) + a shared [256 x 8] block of zeros (K 8..15)
@@ -504,8 +506,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         // tile -> (image n, slice s, tile origin); depth / focus of this thread's pixel are fetched
         // one tile ahead so that layer 0 (the head of the serial chain) never waits on HBM
         auto tile_coords = [&](long long tile, int& n, int& s, int& h0, int& w0) {
-            const int txy = (int)(tile % tiles_xy);
-            const long long ns = tile / tiles_xy;
+            const long long gt = tile + P.tile0;
+            const int txy = (int)(gt % tiles_xy);
+            const long long ns = gt / tiles_xy;
             s = (int)(ns % ra.S);
             n = (int)(ns / ra.S);
             h0 = (txy / P.tiles_x) * TC_TILE_H;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void f32_tile(const float* __restrict__ wt, const flo
 template <bool RENDER>
 __global__ void __launch_bounds__(F32_NT, 1)
 mlp_fp32_kernel(Fp32Net net, RenderArgs ra, const float* __restrict__ probes, float* __restrict__ psf_out,
-                long long M) {
+                long long M0, long long M) {     // flat pixel*slice (or probe) ids [M0, M)
     extern __shared__ __align__(16) float sm[];
     float* buf0 = sm;
     float* buf1 = sm + 256 * F32_TP;
@@ -65,7 +65,7 @@ mlp_fp32_kernel(Fp32Net net, RenderArgs ra, const float* __restrict__ probes, fl
     const int gp = t & 63, part = t >> 6;     // gather-phase mapping
     const int kk = net.kk;
 
-    for (long long base = (long long)blockIdx.x * F32_TP; base < M; base += (long long)gridDim.x * F32_TP) {
+    for (long long base = M0 + (long long)blockIdx.x * F32_TP; base < M; base += (long long)gridDim.x * F32_TP) {
         // ---- network input (x, y, z, foc_z) -> buf0[0..3][p]
         if (t < F32_TP) {
             const long long id = base + t;

@@ -26,7 +26,17 @@ struct ThinLensArgs {
     float foc_len, ps;    // focal length [mm], pixel size [mm]
     float d_lo, d_hi;     // depth clamp: 200, 20000 mm
     int flip;             // 1: depth and foc are negated first (reference: `if (depth < 0).any()`)
+    const unsigned char* flip_dev;   // if not null, the decision is read from device memory (see any_negative_kernel):
+                                     // the reference's data-dependent branch without a device->host round trip
 };
+
+// flag[0] |= any(x < 0)   (the reference's `if (depth < 0).any()`, psfnet.py:504, decided on the device)
+__global__ void __launch_bounds__(256) any_negative_kernel(const float* __restrict__ x, long long n, unsigned char* flag) {
+    bool neg = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        neg |= (__ldg(x + i) < 0.f);
+    if (__syncthreads_or(neg) && threadIdx.x == 0) *flag = 1;     // benign race: every writer stores 1
+}
 
 __global__ void __launch_bounds__(TL_TILE_H * 32)
 thinlens_render_kernel(ThinLensArgs a) {
@@ -38,6 +48,7 @@ thinlens_render_kernel(ThinLensArgs a) {
     const int cstride = HH * pitch;
     const int tiles_x = (a.W + TL_TILE_W - 1) / TL_TILE_W, tiles_y = (a.H + TL_TILE_H - 1) / TL_TILE_H;
     const long long n_tiles = (long long)a.N * tiles_x * tiles_y;
+    const bool flip = a.flip_dev ? (*a.flip_dev != 0) : (a.flip != 0);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
@@ -50,7 +61,7 @@ thinlens_render_kernel(ThinLensArgs a) {
         if (ok) {
             float d = __ldg(a.depth + ((long long)n * a.H + h) * a.W + w);
             float f = __ldg(a.foc + n);
-            if (a.flip) { d = -d; f = -f; }
+            if (flip) { d = -d; f = -f; }
             d = fminf(fmaxf(d, a.d_lo), a.d_hi);
             float coc = a.k1 * fabsf(d - f);
             coc = __fdiv_rn(coc, d);

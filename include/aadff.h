@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AADFF_VERSION 100
+#define AADFF_VERSION 200
 
 #define AADFF_OK 0
 #define AADFF_E_INVALID (-1)      /* bad argument (null pointer, shape, kernel size ...) */
@@ -65,6 +65,18 @@ int aadff_render_stack_f32(aadff_psfnet_t net, const float* img, const float* de
                            const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
                            float d_max, int mode, void* stream);
 
+/* The same for a contiguous run of TILE ROWS -- the unit of the multi-GPU partition ("shard by image,
+ * slice and/or row band"; the reference itself renders on one device, 2_aber_aware_dff_aif.py:108-114).  A tile row is
+ * aadff_tile_row_height() (= 8) image rows of one (image, slice); tile rows are numbered in (image, slice, row) order,
+ * R = (n*S + s)*ceil(H/8) + h/8, and the call renders rows [tile_row_begin, tile_row_end) into `out` (same strides
+ * and base pointer as the full call; everything else is left untouched).  Results are bit-identical to the full call. */
+int aadff_render_stack_rows_f32(aadff_psfnet_t net, const float* img, const float* depth, const float* foc, float* out,
+                                const int64_t out_strides[5], int N, int C, int S, int H, int W, float d_min,
+                                float d_max, int mode, int64_t tile_row_begin, int64_t tile_row_end, void* stream);
+int aadff_tile_row_height(void);
+/* First tensor-core layer group (0 = L1) that AADFF_MODE_ECON evaluates with two MMA terms (bench bookkeeping). */
+int aadff_econ_first_group(void);
+
 /* Same operation with HOST buffers (out is dense [N,C,S,H,W]): copies in, renders, copies
  * out and synchronises, using a workspace and a stream owned by the handle.  This is the call
  * the end-to-end benchmark times.                                                              */
@@ -87,15 +99,20 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
  * circle of confusion -> clipped Gaussian PSF (sigma = coc/2) -> normalise -> per-pixel gather, fused (no PSF
  * tensor in memory).  img [N,C,H,W], depth [N,H,W] mm, foc [N] mm, out [N,C,H,W]; device pointers.
  * pixel_size = sensor_size[0] / sensor_res[0] [mm]; d_lo/d_hi = 200 / 20000 mm (ThinLens.d_min / d_max);
- * flip_sign = 1 negates depth and foc first, which is what the reference does when any depth is negative.   */
+ * flip_sign = 1 negates depth and foc first, which is what the reference does when any depth is negative
+ * (psfnet.py:504).  If flip_sign_dev is not NULL the decision is read from that device byte instead (written by
+ * aadff_any_negative_f32 earlier on the same stream), so the data-dependent branch costs no host synchronisation. */
 int aadff_thinlens_render_f32(const float* img, const float* depth, const float* foc, float* out, int N, int C, int H,
                               int W, int ks, float foc_len, float fnum, float pixel_size, float d_lo, float d_hi,
-                              int flip_sign, void* stream);
+                              int flip_sign, const unsigned char* flip_sign_dev, void* stream);
+/* flag_dev[0] = any(x[i] < 0), i < n; device pointers, stream-ordered.                                          */
+int aadff_any_negative_f32(const float* x, int64_t n, unsigned char* flag_dev, void* stream);
 
 /* Replaces select_focus_dist(depth, num, mode='linear') (dff/utils.py:4-51), the producer of foc_dist in the
  * training loop: per image the minimum over valid (> 0) depths and the maximum depth, then `num` (> 3) focus
  * distances linearly between them, ascending.  depth_m [B, HW] (metres, any unit really), out [B, num]; device.
- * An image without a single valid depth yields +inf (the reference raises on it).                          */
+ * An image without a single valid depth yields NaN in all its `num` entries (the reference raises on it; its
+ * training loop skips such batches, 2_aber_aware_dff_aif.py:103-105).                                      */
 int aadff_select_focus_f32(const float* depth_m, int B, int64_t HW, int num, float* out, void* stream);
 
 /* Number of kernels launched by this library in the calling process (bench bookkeeping).      */

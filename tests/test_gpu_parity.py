@@ -348,6 +348,143 @@ def test_c2_constant_image_is_fixed_point(lens):
         assert float((out - 0.625).abs().max()) < 2e-6, mode
 
 
+# --------------------------------------------------------------------------- BASELINE sizes against the REFERENCE's output
+# (tests/golden/make_golden_baseline_sizes.py ran the reference itself on bench.py's seeded workloads; the inputs are
+#  regenerated here from the same seed).  max-abs is printed (pytest -s / the GPU log) and asserted per mode.
+BASELINE_TOL = {"parity": 2e-5, "econ": 6e-5, "fp32": 5e-6}
+
+
+def _report(tag, mode, err):
+    print(f"[parity-at-size] {tag:28s} mode={mode:7s} max-abs vs reference = {err:.3e}")
+
+
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+def test_c2_full_size_vs_reference_golden(lens, mode):
+    """BASELINE config c2 (1 x 5 x 512 x 512, k = 11), all five slices, vs the reference's PSFNet.render."""
+    g = load_golden("kat_c2_1x5x512x512.npz")
+    img, dm = orc.synthetic_rgbd(1, 512, 512, seed=int(g["seed"]))
+    foc_m = orc.synthetic_focus(dm, 5)
+    assert torch.equal(foc_m, T(g["foc_m"]))
+    out = lens.render_stack(img.cuda(), -dm.cuda() * 1e3, -foc_m.cuda() * 1e3, mode=mode).cpu()
+    err = max(float((out[..., ::4, ::4] - T(g["out_sub"])).abs().max()),
+              float((out[..., [0, 1, 255, 256, 510, 511], :] - T(g["out_rows"])).abs().max()))
+    _report("c2 1x5x512x512 k=11", mode, err)
+    assert err < BASELINE_TOL[mode]
+    assert float((out.double().sum((1, 3, 4)) - T(g["sums"])).abs().max()) < 786432 * (1e-6 if mode == "econ" else 5e-7)   # mean bias over ALL pixels of a slice
+
+
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+def test_c3_full_size_vs_reference_golden(lens, mode):
+    """BASELINE config c3 (16 x 5 x 256 x 256, k = 11): all 16 images, all slices (1/64 of the pixels of every slice,
+    1/4 of image 3, sums over everything); fp32 on images 0..3 only (16.5 Mpix/s kernel)."""
+    g = load_golden("kat_c3_16x5x256x256.npz")
+    img, dm = orc.synthetic_rgbd(16, 256, 256, seed=int(g["seed"]))
+    foc_m = orc.synthetic_focus(dm, 5)
+    assert torch.equal(foc_m, T(g["foc_m"]))
+    n = 4 if mode == "fp32" else 16
+    out = lens.render_stack(img[:n].cuda(), -dm[:n].cuda() * 1e3, -foc_m[:n].cuda() * 1e3, mode=mode).cpu()
+    err = max(float((out[..., ::8, ::8] - T(g["out_sub"])[:n]).abs().max()),
+              float((out[3, :, :, ::2, ::2] - T(g["out_full_img3"])).abs().max()))
+    _report("c3 16x5x256x256 k=11", mode, err)
+    assert err < BASELINE_TOL[mode]
+    assert float((out.double().sum((1, 3, 4)) - T(g["sums"])[:n]).abs().max()) < 196608 * (1e-6 if mode == "econ" else 5e-7)
+
+
+@pytest.fixture(scope="module")
+def lens31_bench(pkg):
+    """bench.py's c4 network: PSFNet(kernel_size=31) with the seeded kaiming-uniform weights, zero biases."""
+    Ws, bs = orc.seeded_psfnet_weights(31, seed=0)
+    l = pkg.PSFNet(kernel_size=31, device="cuda")
+    sd = {}
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        sd[f"net.{2 * i}.weight"], sd[f"net.{2 * i}.bias"] = W, b
+    l.psfnet.load_state_dict(sd)
+    return l
+
+
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+def test_c4_full_size_vs_reference_golden(lens31_bench, mode):
+    """BASELINE config c4 (1 x 10 x 1080 x 1920, k = 31): the whole stack is rendered; the top-border, middle and
+    bottom-border 8-row bands of slices 0, 5, 9 are compared with the reference's banded evaluation (its own
+    PSFNet.pred + local_psf_render on the row-padded full frame, proven bit-equal to a full-frame call where that
+    fits in memory -- see make_golden_baseline_sizes.py)."""
+    g = load_golden("kat_c4_1x10x1080x1920_ks31.npz")
+    img, dm = orc.synthetic_rgbd(1, 1080, 1920, seed=int(g["seed"]))
+    foc_m = orc.synthetic_focus(dm, 10)
+    assert torch.equal(foc_m, T(g["foc_m"]))
+    slices = [int(s) for s in g["slices"]]
+    sel = foc_m[:, slices] if mode == "fp32" else foc_m           # fp32 kernel: only the three compared slices
+    out = lens31_bench.render_stack(img.cuda(), -dm.cuda() * 1e3, -sel.cuda() * 1e3, mode=mode)
+    cs, err = int(g["col_stride"]), 0.0
+    for i, s in enumerate(slices):
+        for (h0, h1) in g["bands"]:
+            got = out[0, :, i if mode == "fp32" else s, int(h0):int(h1), ::cs].cpu()
+            err = max(err, float((got - T(g[f"s{s}_h{int(h0)}"])).abs().max()))
+    _report("c4 1x10x1080x1920 k=31", mode, err)
+    # seeded random weights (no k=31 checkpoint exists): econ's calibration is certified at the north_star bar there
+    assert err < (1e-4 if mode == "econ" else BASELINE_TOL[mode])
+
+
+def test_tile_row_ranges_are_bit_identical_to_the_full_launch(pkg, lens):
+    """aadff_render_stack_rows_f32 (the multi-GPU partition unit): any split of the tile rows reproduces the full
+    launch bit for bit, ragged H included, in the tensor-core and the fp32 kernel."""
+    sh = pkg.sharding
+    for (N, S, H, W) in [(2, 3, 37, 50), (1, 5, 64, 48)]:
+        img, dm = orc.synthetic_rgbd(N, H, W, seed=H)
+        foc = -orc.synthetic_focus(dm, S).cuda() * 1e3
+        img, dep = img.cuda(), -dm.cuda() * 1e3
+        for mode in ("parity", "fp32"):
+            full = lens.render_stack(img, dep, foc, mode=mode)
+            rows_full = full.permute(0, 2, 3, 1, 4).reshape(N * S * H, 3, W)
+            for world in (1, 3, 8):
+                parts = []
+                for r in range(world):
+                    R0, R1 = sh.tile_row_range(N, S, H, world, r)
+                    part = lens.render_stack_rows(img, dep, foc, R0, R1, mode=mode)
+                    assert part.shape[0] == sh.flat_row(R1, H) - sh.flat_row(R0, H)
+                    parts.append(part)
+                assert torch.equal(torch.cat(parts, 0), rows_full), (N, S, H, W, mode, world)
+    nat = pkg.native
+    s = (ctypes.c_int64 * 5)(1, 1, 1, 1, 1)
+    assert nat.lib.aadff_render_stack_rows_f32(lens.native().handle, 8, 8, 8, 8, s, 1, 3, 1, 16, 8, -200.0, -20000.0,
+                                               0, 1, 3, None) == -1            # only 2 tile rows exist
+
+
+def test_thinlens_sign_decided_on_device_and_focus_sentinel(pkg):
+    """ThinLens.render makes the reference's data-dependent sign decision (psfnet.py:504) on the device: no host
+    synchronisation, so the call is CUDA-graph capturable; both sign conventions give the reference's result.
+    select_focus_dist marks an image without valid depth with NaN instead of silently returning +inf."""
+    from deeplens.psfnet import ThinLens
+    from dff.utils import select_focus_dist
+    tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=11, sensor_size=[36.0, 24.0], sensor_res=(40, 56)).to("cuda")
+    gen = torch.Generator().manual_seed(3)
+    img = torch.rand(1, 3, 40, 56, generator=gen).cuda()
+    dep = (300 + 6000 * torch.rand(1, 1, 40, 56, generator=gen)).cuda()
+    foc = torch.tensor([1500.0]).cuda()
+    pos = tl.render(img, dep, foc)
+    neg = tl.render(img, -dep, -foc)
+    assert torch.equal(pos, neg)
+    assert maxabs(pos, orc.thinlens_render(img.cpu(), dep.cpu(), foc.cpu(), 11, 50.0, 1.8, tl.ps)) < 5e-6
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        tl.render(img, -dep, -foc)
+        with torch.cuda.graph(graph, stream=side):
+            captured = tl.render(img, -dep, -foc)
+    torch.cuda.current_stream().wait_stream(side)
+    captured.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, pos)
+    d = torch.rand(3, 1, 16, 16).cuda() + 0.5
+    d[1] = 0.0                                               # image 1: no valid depth at all
+    f = select_focus_dist(d, 5)
+    assert bool(torch.isnan(f[1]).all()) and bool(torch.isfinite(f[[0, 2]]).all())
+    lens = pkg.PSFNet(kernel_size=11, device="cuda")
+    with pytest.raises(ValueError):
+        lens.simulate_focal_stack(torch.rand(3, 3, 16, 16).cuda(), d, 5, check=True)
+
+
 def test_c2_tensor_core_vs_fp32_full_size(lens):
     img, dm = orc.synthetic_rgbd(1, 512, 512, seed=1234)
     foc = -orc.synthetic_focus(dm, 5) * 1e3

@@ -113,3 +113,21 @@ def test_kat_h_thinlens():
     out = orc.thinlens_render(T(g["img"]), -T(g["depth_m"]) * 1e3, T(g["foc"]), 11,
                               float(g["foc_len"]), float(g["fnum"]), float(g["sensor_size"][0]) / 40)
     assert (out - T(g["out"])).abs().max() < TOL
+
+
+def test_oracle_matches_reference_at_baseline_sizes(rf50mm_weights):
+    """The oracle against the reference's own output at BASELINE sizes (one slice of c2, one image of c3):
+    tests/golden/make_golden_baseline_sizes.py ran the reference on bench.py's seeded workloads."""
+    from conftest import load_golden
+    g = load_golden("kat_c2_1x5x512x512.npz")
+    img, dm = orc.synthetic_rgbd(1, 512, 512, seed=int(g["seed"]))
+    foc_m = orc.synthetic_focus(dm, 5)
+    assert torch.equal(foc_m, torch.from_numpy(g["foc_m"]))
+    out = orc.render(*rf50mm_weights, img, -dm * 1e3, -foc_m[:, 2] * 1e3, 11)
+    assert float((out[..., ::4, ::4] - torch.from_numpy(g["out_sub"])[:, :, 2]).abs().max()) < 2e-6
+    assert abs(float(out.double().sum()) - float(g["sums"][0, 2])) < 0.1     # 786 432 values: mean bias < 1.3e-7
+    g = load_golden("kat_c3_16x5x256x256.npz")
+    img, dm = orc.synthetic_rgbd(16, 256, 256, seed=int(g["seed"]))
+    foc_m = orc.synthetic_focus(dm, 5)
+    out = orc.render(*rf50mm_weights, img[3:4], -dm[3:4] * 1e3, -foc_m[3:4, 4] * 1e3, 11)
+    assert float((out[0, :, ::2, ::2] - torch.from_numpy(g["out_full_img3"])[:, 4]).abs().max()) < 2e-6
