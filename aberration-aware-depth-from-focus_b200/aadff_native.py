@@ -79,6 +79,8 @@ def _load() -> ctypes.CDLL:
                                                 ctypes.c_int64, ctypes.c_void_p]
     lib.aadff_tile_row_height.restype = ctypes.c_int
     lib.aadff_econ_first_group.restype = ctypes.c_int
+    lib.aadff_render_psf_map_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + \
+                                            [ctypes.POINTER(ctypes.c_int)] * 2 + [ctypes.c_void_p]
     lib.aadff_any_negative_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     lib.aadff_render_stack_host_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 5 + \
                                                [ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -97,7 +99,7 @@ def _load() -> ctypes.CDLL:
     lib.aadff_select_focus_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]
     for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32", "aadff_render_stack_rows_f32",
-               "aadff_any_negative_f32",
+               "aadff_any_negative_f32", "aadff_render_psf_map_f32",
                "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_psfnet_pred_tc_f32", "aadff_local_psf_render_f32", "aadff_thinlens_render_f32", "aadff_select_focus_f32",
                "aadff_debug_umma_gemm", "aadff_debug_set_desc_swap"):
         getattr(lib, fn).restype = ctypes.c_int

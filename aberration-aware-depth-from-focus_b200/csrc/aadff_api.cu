@@ -18,6 +18,7 @@
 #include "mlp_fp32_kernel.cuh"
 #include "thinlens_kernel.cuh"
 #include "focus_kernel.cuh"
+#include "psf_conv_kernel.cuh"
 #include "econ_calib.h"
 
 using namespace aadff;
@@ -61,6 +62,19 @@ bool launch_gc_ks(int ks, int cn, int grid, cudaStream_t st, const float* img, c
 bool launch_gather_coalesced(int ks, int cn, int grid, cudaStream_t st, const float* img, const float* psf, float* out,
                              int N, int C, int H, int W, int c0) {
     return launch_gc_ks<3>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
+}
+
+template <int KS>
+bool launch_psf_conv(int ks, int grid, cudaStream_t st, const PsfConvArgs& a) {
+    if constexpr (KS > 31) {
+        return false;
+    } else {
+        if (ks == KS) {
+            psf_conv_kernel<KS><<<grid, PC_NT, 0, st>>>(a);
+            return true;
+        }
+        return launch_psf_conv<KS + 2>(ks, grid, st, a);
+    }
 }
 
 #define CUDA_TRY(expr)                                                                          \
@@ -749,6 +763,37 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
+    return AADFF_OK;
+}
+
+int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out, int B, int C, int H, int W, int ks,
+                             int grid, const int* row_bounds, const int* col_bounds, void* stream) {
+    if (!img || !psf_map || !out || !row_bounds || !col_bounds) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (ks < 1 || ks > 31 || (ks % 2) == 0) return fail(AADFF_E_INVALID, "PSF kernel size should be odd (and <= 31)");
+    if (grid < 1 || grid > PC_MAX_GRID) return fail(AADFF_E_INVALID, "grid must be in [1, 32]");
+    if ((ks - 1) / 2 >= H || (ks - 1) / 2 >= W) return fail(AADFF_E_INVALID, "reflect padding needs (ks-1)/2 < H, W");
+    if (B == 0) return AADFF_OK;
+    PsfConvArgs a{};
+    a.img = img; a.psf_map = psf_map; a.out = out;
+    a.B = B; a.C = C; a.H = H; a.W = W; a.grid = grid;
+    for (int i = 0; i <= grid; ++i) { a.hb[i] = row_bounds[i]; a.wb[i] = col_bounds[i]; }
+    if (a.hb[0] != 0 || a.wb[0] != 0 || a.hb[grid] > H || a.wb[grid] > W) return fail(AADFF_E_INVALID, "bad patch bounds");
+    for (int i = 0; i < grid; ++i) {
+        if (a.hb[i + 1] < a.hb[i] || a.wb[i + 1] < a.wb[i]) return fail(AADFF_E_INVALID, "patch bounds must ascend");
+        a.max_ch = std::max(a.max_ch, a.hb[i + 1] - a.hb[i]);
+        a.max_cw = std::max(a.max_cw, a.wb[i + 1] - a.wb[i]);
+    }
+    if (a.max_ch == 0 || a.max_cw == 0) return AADFF_OK;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (long long)B * C * grid * grid * ((a.max_ch + PC_TILE_H - 1) / PC_TILE_H) *
+                            ((a.max_cw + PC_TILE_W - 1) / PC_TILE_W);
+    const int nblk = (int)std::min<long long>(tiles, (long long)sms * 8);
+    if (!launch_psf_conv<1>(ks, nblk, static_cast<cudaStream_t>(stream), a)) return fail(AADFF_E_INVALID, "unsupported kernel size");
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
 }
 

@@ -108,6 +108,14 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
 /* flag_dev[0] = any(x[i] < 0), i < n; device pointers, stream-ordered.                                          */
 int aadff_any_negative_f32(const float* x, int64_t n, unsigned char* flag_dev, void* stream);
 
+/* Replaces render_psf (deeplens/render_psf.py:12-28; grid = 1, psf_map = [C,ks,ks], bounds {0,H} / {0,W}) and
+ * render_psf_map (deeplens/render_psf.py:31-73; psf_map = [C, grid*ks, grid*ks], one PSF per image patch): true
+ * convolution (the PSF is flipped) on the reflect-padded image, per channel.  row_bounds / col_bounds are HOST arrays of
+ * grid+1 ascending patch limits (the reference's int(i/grid*H), int(j/grid*W)); rows/columns beyond the last limit are
+ * left untouched, as in the reference.  ks odd, <= 31; grid <= 32; img, psf_map, out are device pointers.        */
+int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out, int B, int C, int H, int W, int ks,
+                             int grid, const int* row_bounds, const int* col_bounds, void* stream);
+
 /* Replaces select_focus_dist(depth, num, mode='linear') (dff/utils.py:4-51), the producer of foc_dist in the
  * training loop: per image the minimum over valid (> 0) depths and the maximum depth, then `num` (> 3) focus
  * distances linearly between them, ascending.  depth_m [B, HW] (metres, any unit really), out [B, num]; device.

@@ -271,6 +271,32 @@ def test_thinlens_and_focus_golden(pkg):
     assert torch.equal(select_focus_dist(big.cuda(), 7).cpu(), orc.select_focus_dist(big, 7))
 
 
+def test_render_psf_and_psf_map_golden(pkg):
+    """f4 row: render_psf / render_psf_map (deeplens/render_psf.py:12-73) -- reflect padding, flipped PSF, per-channel
+    PSFs, grid of patches with int(i/grid*H) bounds (non-divisible sizes) -- against the reference's own outputs."""
+    from deeplens.render_psf import render_psf, render_psf_map, local_psf_render_high_res, local_psf_render
+    g = load_golden("kat_i_psf_conv.npz")
+    for i in range(4):
+        out = render_psf(T(g[f"conv{i}_img"]).cuda(), T(g[f"conv{i}_psf"]).cuda())
+        assert out.shape == g[f"conv{i}_out"].shape and maxabs(out, T(g[f"conv{i}_out"])) < 2e-6, i
+    for i in range(3):
+        out = render_psf_map(T(g[f"map{i}_img"]).cuda(), T(g[f"map{i}_psf"]).cuda(), int(g[f"map{i}_grid"]))
+        ks = g[f"map{i}_psf"].shape[1] // int(g[f"map{i}_grid"])
+        assert maxabs(out, T(g[f"map{i}_out"])) < 2e-6 * ks * ks, i          # un-normalised random PSFs: sums up to ks^2/2
+    with pytest.raises(ValueError):
+        render_psf(torch.rand(1, 3, 8, 8).cuda(), torch.rand(3, 4, 4).cuda())
+    # the patch-wise gather keeps the reference's semantics: each patch replicate-padded on its own
+    gen = torch.Generator().manual_seed(9)
+    img, psf = torch.rand(1, 3, 40, 50, generator=gen), torch.rand(1, 40, 50, 5, 5, generator=gen)
+    hi = local_psf_render_high_res(img.cuda(), psf.cuda(), patch_size=[16, 32], kernel_size=5)
+    ref = torch.zeros_like(img)
+    for (a, b) in [(0, 16), (16, 32), (32, 40)]:
+        for (c, d) in [(0, 32), (32, 50)]:
+            ref[:, :, a:b, c:d] = orc.local_psf_render(img[:, :, a:b, c:d], psf[:, a:b, c:d], 5)
+    assert maxabs(hi, ref) < 2e-6
+    assert maxabs(hi, local_psf_render(img.cuda(), psf.cuda(), 5)) > 1e-3        # ... which is NOT the full-frame gather
+
+
 # --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
 @pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 3, 9, 1), (1, 3, 1, 21), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17),
                                      (2, 3, 7, 130)])
