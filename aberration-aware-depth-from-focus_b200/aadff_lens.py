@@ -236,6 +236,52 @@ class PSFNet(nn.Module):
         stack = PSFNet.render_stack(self, aif, -depth_m * 1e3, -focus_dists * 1e3, layout=layout, mode=mode)
         return stack, focus_dists
 
+    # ------------------------------------------------------------------ fitting
+    def train_psfnet(self, iters=10000, bs=128, lr=1e-4, spp=2048, evaluate_every=1000, result_dir='./results/temp',
+                     data=None, save=True):
+        """Fit the PSF representation network (mirror of deeplens/psfnet.py:79-132).  The optimisation --
+        psfnet(inp), nn.MSELoss, backward, AdamW with CosineAnnealingLR(T_max=iters) -- runs on the device as one
+        CUDA-graph replay per iteration (csrc/train_kernels.cuh).  The training targets are ray-traced PSFs
+        (get_training_data, psfnet.py:135-170) and stay with the reference: ``data(bs=, spp=)`` must return
+        ``(inp [bs,4], psf [bs,ks*ks])``; by default ``self.get_training_data`` is used, which exists when these
+        methods are grafted onto the reference's PSFNet (aadff_install.install()).  Returns the list of losses
+        recorded every ``evaluate_every`` iterations (the reference plots PSFs there)."""
+        import math
+        data = data or getattr(self, "get_training_data", None)
+        if data is None:
+            raise NotImplementedError("train_psfnet needs `data`: ray-traced training targets come from the reference "
+                                      "(PSFNet.get_training_data); this build does not contain the ray tracer")
+        layers = _linear_layers(self.psfnet)
+        idx = _device_index(layers[0].weight.device)
+        dev = torch.device(f"cuda:{idx}")
+        trainer = _nat.NativeTrainer([l.weight.detach().float().cpu().numpy() for l in layers],
+                                     [l.bias.detach().float().cpu().numpy() for l in layers], bs, idx)
+        loss_dev = torch.zeros(1, device=dev)
+        history = []
+        try:
+            with torch.cuda.device(dev):
+                for i in range(iters + 1):
+                    inp, psf = data(bs=bs, spp=spp)
+                    inp = inp.detach().to(dev, torch.float32).reshape(bs, 4).contiguous()
+                    psf = psf.detach().to(dev, torch.float32).reshape(bs, -1).contiguous()
+                    lr_i = 0.5 * lr * (1.0 + math.cos(math.pi * i / iters)) if iters > 0 else lr   # CosineAnnealingLR, eta_min 0
+                    _nat.check(_nat.lib.aadff_trainer_step(trainer.handle, inp.data_ptr(), psf.data_ptr(), lr_i,
+                                                           loss_dev.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                    if (i + 1) % evaluate_every == 0:
+                        history.append((i + 1, float(loss_dev)))
+                ws, bs_ = trainer.read(0, torch.cuda.current_stream().cuda_stream)
+            with torch.no_grad():
+                for l, w, b in zip(layers, ws, bs_):
+                    l.weight.copy_(torch.from_numpy(w))
+                    l.bias.copy_(torch.from_numpy(b))
+            self._native = None
+        finally:
+            trainer.close()
+        if save:
+            os.makedirs(result_dir, exist_ok=True)
+            torch.save(self.psfnet.state_dict(), f'{result_dir}/PSFNet_{getattr(self, "model_name", "mlp")}.pkl')
+        return history
+
     # ------------------------------------------------------------------ utils
     def depth2z(self, depth):
         z = (depth - self.d_min) / (self.d_max - self.d_min)
@@ -247,7 +293,7 @@ class PSFNet(nn.Module):
 
 # names install() grafts onto the reference's PSFNet (everything render/pred need, nothing the ray tracer owns)
 PSFNET_GRAFT = ("native", "refresh", "_mlp_eval", "pred", "_launch", "_prep", "render", "render_stack",
-                "render_stack_rows", "simulate_focal_stack")
+                "render_stack_rows", "simulate_focal_stack", "train_psfnet")
 
 
 class ThinLens(nn.Module):

@@ -81,6 +81,14 @@ def _load() -> ctypes.CDLL:
     lib.aadff_econ_first_group.restype = ctypes.c_int
     lib.aadff_render_psf_map_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + \
                                             [ctypes.POINTER(ctypes.c_int)] * 2 + [ctypes.c_void_p]
+    lib.aadff_trainer_create.argtypes = [ctypes.POINTER(c_f32p), ctypes.POINTER(c_f32p), ctypes.POINTER(ctypes.c_int),
+                                         ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 4 + \
+                                        [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.aadff_trainer_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+    lib.aadff_trainer_read.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(c_f32p), ctypes.POINTER(c_f32p),
+                                       ctypes.c_void_p]
+    lib.aadff_trainer_destroy.argtypes = [ctypes.c_void_p]
     lib.aadff_any_negative_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     lib.aadff_render_stack_host_f32.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 5 + \
                                                [ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -99,7 +107,8 @@ def _load() -> ctypes.CDLL:
     lib.aadff_select_focus_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]
     for fn in ("aadff_psfnet_create", "aadff_psfnet_destroy", "aadff_render_stack_f32", "aadff_render_stack_rows_f32",
-               "aadff_any_negative_f32", "aadff_render_psf_map_f32",
+               "aadff_any_negative_f32", "aadff_render_psf_map_f32", "aadff_trainer_create", "aadff_trainer_step",
+               "aadff_trainer_read", "aadff_trainer_destroy",
                "aadff_render_stack_host_f32", "aadff_psfnet_pred_f32", "aadff_psfnet_pred_tc_f32", "aadff_local_psf_render_f32", "aadff_thinlens_render_f32", "aadff_select_focus_f32",
                "aadff_debug_umma_gemm", "aadff_debug_set_desc_swap"):
         getattr(lib, fn).restype = ctypes.c_int
@@ -150,6 +159,49 @@ class NativePSFNet:
     def close(self):
         if getattr(self, "handle", None):
             lib.aadff_psfnet_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NativeTrainer:
+    """Owns an aadff_trainer_t: device parameters + AdamW state + one batch of activations (include/aadff.h)."""
+
+    def __init__(self, weights, biases, batch: int, device_index: int, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=1e-2):
+        import numpy as np
+        self._np = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        self._nb = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+        n = len(self._np)
+        self.dims = [self._np[0].shape[1]] + [w.shape[0] for w in self._np]
+        self.batch, self.device_index = int(batch), device_index
+        c_f32p = ctypes.POINTER(ctypes.c_float)
+        wp = (c_f32p * n)(*[w.ctypes.data_as(c_f32p) for w in self._np])
+        bp = (c_f32p * n)(*[b.ctypes.data_as(c_f32p) for b in self._nb])
+        dm = (ctypes.c_int * (n + 1))(*self.dims)
+        self.handle = ctypes.c_void_p()
+        check(lib.aadff_trainer_create(wp, bp, dm, n, self.batch, betas[0], betas[1], eps, weight_decay, device_index,
+                                       ctypes.byref(self.handle)))
+
+    def read(self, which: int, stream=None):
+        """which 0: parameters, 1: gradients of the last step -> (weights, biases) as numpy arrays."""
+        import numpy as np
+        n = len(self.dims) - 1
+        ws = [np.empty((self.dims[l + 1], self.dims[l]), np.float32) for l in range(n)]
+        bs = [np.empty((self.dims[l + 1],), np.float32) for l in range(n)]
+        c_f32p = ctypes.POINTER(ctypes.c_float)
+        wp = (c_f32p * n)(*[w.ctypes.data_as(c_f32p) for w in ws])
+        bp = (c_f32p * n)(*[b.ctypes.data_as(c_f32p) for b in bs])
+        check(lib.aadff_trainer_read(self.handle, which, wp, bp, stream))
+        return ws, bs
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.aadff_trainer_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

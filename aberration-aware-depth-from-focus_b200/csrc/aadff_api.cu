@@ -19,6 +19,7 @@
 #include "thinlens_kernel.cuh"
 #include "focus_kernel.cuh"
 #include "psf_conv_kernel.cuh"
+#include "train_kernels.cuh"
 #include "econ_calib.h"
 
 using namespace aadff;
@@ -167,6 +168,73 @@ struct aadff_psfnet {
     float* ws = nullptr;
     size_t ws_bytes = 0;
 };
+
+// ------------------------------------------------------------------------------------------ PSFNet fitting (f3)
+struct aadff_trainer {
+    int device = 0, n_layers = 0, batch = 0, kk = 0;
+    std::vector<int> dims;
+    std::vector<size_t> w_off, b_off;          // float offsets into params / grads
+    size_t n_params = 0;
+    float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+    std::vector<float*> act;                   // act[l] = input of layer l, [batch, dims[l]]
+    float *z = nullptr, *p = nullptr, *target = nullptr, *dz[2] = {nullptr, nullptr}, *loss = nullptr;
+    AdamHyper* hyper = nullptr;
+    AdamHyper host_hyper{};
+    long long step = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap_stream = nullptr;
+};
+
+static void trainer_free(aadff_trainer* t) {
+    if (!t) return;
+    DeviceGuard guard(t->device);
+    if (t->exec) cudaGraphExecDestroy(t->exec);
+    if (t->graph) cudaGraphDestroy(t->graph);
+    if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    for (float* a : t->act) cudaFree(a);
+    cudaFree(t->params); cudaFree(t->grads); cudaFree(t->m); cudaFree(t->v);
+    cudaFree(t->z); cudaFree(t->p); cudaFree(t->target); cudaFree(t->dz[0]); cudaFree(t->dz[1]);
+    cudaFree(t->loss); cudaFree(t->hyper);
+    delete t;
+}
+
+template <int EPI>
+static void tg_launch(cudaStream_t st, const float* A, long long sa_i, long long sa_k, const float* B, long long sb_k,
+                      long long sb_j, float* C, int M, int N, int K, const float* aux) {
+    dim3 grid((N + TG_TILE - 1) / TG_TILE, (M + TG_TILE - 1) / TG_TILE);
+    train_gemm_kernel<EPI><<<grid, TG_NT, 0, st>>>(A, sa_i, sa_k, B, sb_k, sb_j, C, M, N, K, aux);
+}
+
+// the whole step (forward, loss, backward, AdamW) as a stream of launches: recorded once into a CUDA graph
+static int trainer_record(aadff_trainer* t, cudaStream_t st) {
+    const int L = t->n_layers, M = t->batch;
+    for (int l = 0; l < L; ++l) {
+        const int K = t->dims[l], N = t->dims[l + 1];
+        const float* W = t->params + t->w_off[l];
+        const float* b = t->params + t->b_off[l];
+        if (l < L - 1) tg_launch<TG_BIAS_RELU>(st, t->act[l], K, 1, W, 1, K, t->act[l + 1], M, N, K, b);
+        else tg_launch<TG_BIAS>(st, t->act[l], K, 1, W, 1, K, t->z, M, N, K, b);
+    }
+    train_head_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(t->z, t->target, t->p, t->dz[0], t->loss, M, t->kk);
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = t->dims[l], N = t->dims[l + 1];
+        const float* W = t->params + t->w_off[l];
+        const float* dZ = t->dz[cur];
+        tg_launch<TG_PLAIN>(st, dZ, 1, N, t->act[l], K, 1, t->grads + t->w_off[l], N, K, M, nullptr);      // dW = dZ^T X
+        train_colsum_kernel<<<(N + 255) / 256, 256, 0, st>>>(dZ, t->grads + t->b_off[l], M, N);
+        if (l > 0) {
+            tg_launch<TG_RELU_MASK>(st, dZ, N, 1, W, K, 1, t->dz[cur ^ 1], M, K, N, t->act[l]);            // dX = dZ W, masked
+            cur ^= 1;
+        }
+    }
+    train_adamw_kernel<<<(int)std::min<size_t>((t->n_params + 255) / 256, 1184), 256, 0, st>>>(
+        t->params, t->grads, t->m, t->v, (long long)t->n_params, t->hyper);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
 
 extern "C" {
 
@@ -805,6 +873,108 @@ int aadff_select_focus_f32(const float* depth_m, int B, int64_t HW, int num, flo
     select_focus_kernel<<<B, FOCUS_NT, 0, static_cast<cudaStream_t>(stream)>>>(depth_m, (long long)HW, num, out);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+
+int aadff_trainer_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
+                         int batch, float beta1, float beta2, float eps, float weight_decay, int device,
+                         aadff_trainer_t* out) {
+    if (!weights || !biases || !dims || !out) return fail(AADFF_E_INVALID, "null argument");
+    if (n_layers < 1 || n_layers > MAX_LAYERS || batch < 1) return fail(AADFF_E_INVALID, "bad n_layers / batch");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select CUDA device " + std::to_string(device));
+    aadff_trainer* t = new aadff_trainer();
+    t->device = device; t->n_layers = n_layers; t->batch = batch; t->kk = dims[n_layers];
+    t->dims.assign(dims, dims + n_layers + 1);
+    t->host_hyper.beta1 = beta1; t->host_hyper.beta2 = beta2; t->host_hyper.eps = eps; t->host_hyper.weight_decay = weight_decay;
+    size_t off = 0;
+    int wmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        t->w_off.push_back(off); off += (size_t)dims[l] * dims[l + 1];
+        t->b_off.push_back(off); off += (size_t)dims[l + 1];
+        wmax = std::max(wmax, std::max(dims[l], dims[l + 1]));
+    }
+    t->n_params = off;
+#define TR_TRY(expr)                                                                             \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            trainer_free(t);                                                                     \
+            return fail(AADFF_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+        }                                                                                        \
+    } while (0)
+    auto dalloc = [&](float** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float)); };
+    TR_TRY(dalloc(&t->params, off)); TR_TRY(dalloc(&t->grads, off)); TR_TRY(dalloc(&t->m, off)); TR_TRY(dalloc(&t->v, off));
+    TR_TRY(cudaMemset(t->m, 0, off * sizeof(float))); TR_TRY(cudaMemset(t->v, 0, off * sizeof(float)));
+    for (int l = 0; l < n_layers; ++l) {
+        if (!weights[l] || !biases[l]) { trainer_free(t); return fail(AADFF_E_INVALID, "null layer pointer"); }
+        TR_TRY(cudaMemcpy(t->params + t->w_off[l], weights[l], (size_t)dims[l] * dims[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
+        TR_TRY(cudaMemcpy(t->params + t->b_off[l], biases[l], (size_t)dims[l + 1] * sizeof(float), cudaMemcpyHostToDevice));
+        float* a = nullptr;
+        TR_TRY(dalloc(&a, (size_t)batch * dims[l]));
+        t->act.push_back(a);
+    }
+    TR_TRY(dalloc(&t->z, (size_t)batch * t->kk)); TR_TRY(dalloc(&t->p, (size_t)batch * t->kk));
+    TR_TRY(dalloc(&t->target, (size_t)batch * t->kk));
+    TR_TRY(dalloc(&t->dz[0], (size_t)batch * wmax)); TR_TRY(dalloc(&t->dz[1], (size_t)batch * wmax));
+    TR_TRY(dalloc(&t->loss, 1));
+    TR_TRY(cudaMalloc(reinterpret_cast<void**>(&t->hyper), sizeof(AdamHyper)));
+    TR_TRY(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+    TR_TRY(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = trainer_record(t, t->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(t->cap_stream, &t->graph);
+    if (rc != AADFF_OK || ce != cudaSuccess) { trainer_free(t); return rc ? rc : fail(AADFF_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce)); }
+    TR_TRY(cudaGraphInstantiate(&t->exec, t->graph, 0));
+#undef TR_TRY
+    *out = t;
+    return AADFF_OK;
+}
+
+int aadff_trainer_destroy(aadff_trainer_t t) {
+    trainer_free(t);
+    return AADFF_OK;
+}
+
+int aadff_trainer_step(aadff_trainer_t t, const float* inp, const float* target, float lr, float* loss_out, void* stream) {
+    if (!t || !inp || !target) return fail(AADFF_E_INVALID, "null argument");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t M = (size_t)t->batch;
+    CUDA_TRY(cudaMemcpyAsync(t->act[0], inp, M * t->dims[0] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t->target, target, M * t->kk * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    t->step += 1;
+    AdamHyper h = t->host_hyper;
+    h.lr = lr;
+    h.bias_correction1 = (float)(1.0 - std::pow((double)h.beta1, (double)t->step));
+    h.bias_correction2_sqrt = (float)std::sqrt(1.0 - std::pow((double)h.beta2, (double)t->step));
+    train_hyper_kernel<<<1, 1, 0, st>>>(t->hyper, h, t->loss);
+    CUDA_TRY(cudaGraphLaunch(t->exec, st));
+    g_launches.fetch_add(2 + 3 * t->n_layers * 2);
+    if (loss_out) CUDA_TRY(cudaMemcpyAsync(loss_out, t->loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+// which: 0 = parameters, 1 = gradients of the last step, 2 = the last step's predicted PSFs (p into weights[0], [batch, kk])
+int aadff_trainer_read(aadff_trainer_t t, int which, float* const* weights, float* const* biases, void* stream) {
+    if (!t || !weights) return fail(AADFF_E_INVALID, "null argument");
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return fail(AADFF_E_CUDA, "cannot select device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (which == 2) {
+        CUDA_TRY(cudaMemcpy(weights[0], t->p, (size_t)t->batch * t->kk * sizeof(float), cudaMemcpyDeviceToHost));
+        return AADFF_OK;
+    }
+    if (which != 0 && which != 1) return fail(AADFF_E_INVALID, "which must be 0, 1 or 2");
+    if (!biases) return fail(AADFF_E_INVALID, "null argument");
+    const float* src = which == 0 ? t->params : t->grads;
+    for (int l = 0; l < t->n_layers; ++l) {
+        CUDA_TRY(cudaMemcpy(weights[l], src + t->w_off[l], (size_t)t->dims[l] * t->dims[l + 1] * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(biases[l], src + t->b_off[l], (size_t)t->dims[l + 1] * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     return AADFF_OK;
 }
 

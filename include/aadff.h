@@ -123,6 +123,24 @@ int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out,
  * training loop skips such batches, 2_aber_aware_dff_aif.py:103-105).                                      */
 int aadff_select_focus_f32(const float* depth_m, int B, int64_t HW, int num, float* out, void* stream);
 
+/* Replaces the optimisation half of PSFNet.train_psfnet (deeplens/psfnet.py:79-132): `psfnet(inp)` ->
+ * nn.MSELoss()(pred, psf) -> loss.backward() -> torch.optim.AdamW.step(), fp32, for MLP(4, ks*ks, 256, n) -- the
+ * training targets (ray-traced PSFs, psfnet.py:135-170) stay with the caller.  The trainer owns a device copy of the
+ * parameters (weights/biases/dims as for aadff_psfnet_create, HOST pointers), their AdamW state and the activations of
+ * one batch of `batch` probes; one step is a CUDA graph replay (3 kernels per layer and direction + head + AdamW).
+ *   aadff_trainer_step: inp [batch,4], target [batch,ks*ks] device pointers; lr = this step's learning rate (the
+ *     reference drives it with CosineAnnealingLR); loss_out = optional DEVICE scalar receiving the MSE loss of the
+ *     forward pass that preceded the update.  Stream-ordered, no synchronisation.
+ *   aadff_trainer_read: which = 0 parameters / 1 gradients of the last step into HOST arrays shaped like the
+ *     create call's; which = 2: the last step's predicted PSFs [batch, ks*ks] into weights[0].  Synchronises.   */
+typedef struct aadff_trainer* aadff_trainer_t;
+int aadff_trainer_create(const float* const* weights, const float* const* biases, const int* dims, int n_layers,
+                         int batch, float beta1, float beta2, float eps, float weight_decay, int device,
+                         aadff_trainer_t* out);
+int aadff_trainer_step(aadff_trainer_t t, const float* inp, const float* target, float lr, float* loss_out, void* stream);
+int aadff_trainer_read(aadff_trainer_t t, int which, float* const* weights, float* const* biases, void* stream);
+int aadff_trainer_destroy(aadff_trainer_t t);
+
 /* Number of kernels launched by this library in the calling process (bench bookkeeping).      */
 int64_t aadff_launch_count(void);
 

@@ -297,6 +297,71 @@ def test_render_psf_and_psf_map_golden(pkg):
     assert maxabs(hi, local_psf_render(img.cuda(), psf.cuda(), 5)) > 1e-3        # ... which is NOT the full-frame gather
 
 
+def test_train_psfnet_matches_torch_autograd(pkg):
+    """f3 row: forward + MSE + backward + AdamW of PSFNet.train_psfnet (deeplens/psfnet.py:79-132) on the device
+    against the same step in fp32 torch on the CPU (the reference's operators: nn.Linear/ReLU/Sigmoid/F.normalize,
+    nn.MSELoss, torch.optim.AdamW): gradients of the first step, then parameters and losses over several steps."""
+    import torch.nn as nn
+    nat = pkg.native
+    ks, bs = 11, 128
+    Ws, Bs = orc.seeded_psfnet_weights(ks, seed=3)
+    gen = torch.Generator().manual_seed(17)
+    Bs = [(torch.rand(b.shape, generator=gen) - 0.5) * 0.2 for b in Bs]
+    dims = [4, 64, 256] + [256] * 8 + [ks * ks]
+    mods = []
+    for a, b in zip(dims[:-2], dims[1:-1]):
+        mods += [nn.Linear(a, b), nn.ReLU(inplace=True)]
+    mods += [nn.Linear(dims[-2], dims[-1]), nn.Sigmoid()]
+    net = nn.Sequential(*mods)
+    with torch.no_grad():
+        for lin, W, b in zip([m for m in net if isinstance(m, nn.Linear)], Ws, Bs):
+            lin.weight.copy_(W)
+            lin.bias.copy_(b)
+    opt = torch.optim.AdamW(net.parameters(), 1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=8, eta_min=0)
+    trainer = nat.NativeTrainer([w.numpy() for w in Ws], [b.numpy() for b in Bs], bs, 0)
+    loss_dev = torch.zeros(1, device="cuda")
+    for it in range(5):
+        inp = torch.rand(bs, 4, generator=gen)
+        inp[:, :2] = inp[:, :2] * 2 - 1
+        tgt = torch.rand(bs, ks * ks, generator=gen)
+        tgt = tgt / tgt.sum(1, keepdim=True)
+        pred = torch.nn.functional.normalize(net(inp), p=1, dim=-1)
+        opt.zero_grad()
+        loss = nn.MSELoss()(pred, tgt)
+        loss.backward()
+        lr_i = opt.param_groups[0]["lr"]
+        nat.check(nat.lib.aadff_trainer_step(trainer.handle, inp.cuda().data_ptr(), tgt.cuda().data_ptr(), lr_i,
+                                             loss_dev.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert abs(float(loss_dev) - float(loss)) < 1e-6 * max(1.0, float(loss)) + 1e-9, it
+        if it == 0:
+            gw, gb = trainer.read(1)
+            for lin, a, b in zip([m for m in net if isinstance(m, nn.Linear)], gw, gb):
+                scale = float(lin.weight.grad.abs().max()) + 1e-12
+                assert float((torch.from_numpy(a) - lin.weight.grad).abs().max()) < 2e-5 * scale
+                assert float((torch.from_numpy(b) - lin.bias.grad).abs().max()) < 2e-5 * (float(lin.bias.grad.abs().max()) + 1e-12)
+        opt.step()
+        sched.step()
+    pw, pb = trainer.read(0)
+    for lin, a, b in zip([m for m in net if isinstance(m, nn.Linear)], pw, pb):
+        # AdamW moves every weight by ~lr per step whatever the gradient's size: agreement to a small fraction of lr
+        assert float((torch.from_numpy(a) - lin.weight.detach()).abs().max()) < 2e-5
+        assert float((torch.from_numpy(b) - lin.bias.detach()).abs().max()) < 2e-5
+    trainer.close()
+    # the Python surface: a fit on synthetic targets lowers the loss and writes the weights back
+    lens = pkg.PSFNet(kernel_size=ks, device="cuda")
+    target_net = pkg.PSFNet(kernel_size=ks, device="cuda")
+    def data(bs, spp):
+        x = torch.rand(bs, 4, device="cuda")
+        x[:, :2] = x[:, :2] * 2 - 1
+        return x, target_net.pred(x).reshape(bs, -1)
+    before = [p.detach().clone() for p in lens.psfnet.parameters()]
+    hist = lens.train_psfnet(iters=300, bs=128, lr=1e-3, evaluate_every=100, data=data, save=False)
+    assert len(hist) == 3 and hist[-1][1] < hist[0][1]
+    assert any(not torch.equal(a, b) for a, b in zip(before, lens.psfnet.parameters()))
+
+
 # --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
 @pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 3, 9, 1), (1, 3, 1, 21), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17),
                                      (2, 3, 7, 130)])
