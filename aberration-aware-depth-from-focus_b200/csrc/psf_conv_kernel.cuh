@@ -35,7 +35,8 @@ struct PsfConvArgs {
 
 __device__ __forceinline__ int reflect_index(int p, int n) {      // F.pad(mode='reflect'): -1 -> 1, n -> n-2
     p = p < 0 ? -p : p;
-    return p >= n ? 2 * (n - 1) - p : p;
+    p = p >= n ? 2 * (n - 1) - p : p;
+    return min(max(p, 0), n - 1);          // rows/columns of a tile that lie beyond the image (never used) stay in range
 }
 
 template <int KS>

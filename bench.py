@@ -508,7 +508,7 @@ def run_ours(args):
     strong = {}
     if world > 1 and not args.no_strong:
         for name in ("c3", "c4"):
-            strong[name] = strong_scaling(aadff_b200, dist, name, args.mode, local, rank, world, max(3, args.steps // 4), flush)
+            strong[name] = strong_scaling(aadff_b200, dist, name, args.mode, local, rank, world, max(5, args.steps // 2), flush)
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:

@@ -293,7 +293,7 @@ def test_render_psf_and_psf_map_golden(pkg):
     for (a, b) in [(0, 16), (16, 32), (32, 40)]:
         for (c, d) in [(0, 32), (32, 50)]:
             ref[:, :, a:b, c:d] = orc.local_psf_render(img[:, :, a:b, c:d], psf[:, a:b, c:d], 5)
-    assert maxabs(hi, ref) < 2e-6
+    assert maxabs(hi, ref) < 2e-5                                                # un-normalised 5x5 PSFs: values ~ 8
     assert maxabs(hi, local_psf_render(img.cuda(), psf.cuda(), 5)) > 1e-3        # ... which is NOT the full-frame gather
 
 
@@ -331,7 +331,8 @@ def test_train_psfnet_matches_torch_autograd(pkg):
         loss = nn.MSELoss()(pred, tgt)
         loss.backward()
         lr_i = opt.param_groups[0]["lr"]
-        nat.check(nat.lib.aadff_trainer_step(trainer.handle, inp.cuda().data_ptr(), tgt.cuda().data_ptr(), lr_i,
+        inp_d, tgt_d = inp.cuda(), tgt.cuda()            # (keep both alive: a freed temporary's block would be reused)
+        nat.check(nat.lib.aadff_trainer_step(trainer.handle, inp_d.data_ptr(), tgt_d.data_ptr(), lr_i,
                                              loss_dev.data_ptr(), None))
         torch.cuda.synchronize()
         assert abs(float(loss_dev) - float(loss)) < 1e-6 * max(1.0, float(loss)) + 1e-9, it
