@@ -314,6 +314,70 @@ def stage_rows():
         print(f"pred M=1Mi k11 (tensor-core, {mode}): {ms:.3f} ms  {inp.shape[0] / ms / 1e3:.1f} Mprobes/s", flush=True)
 
 
+def stage_rows2():
+    """Round-2 rows: thin-lens with its bytes-based roofline, render_psf / render_psf_map (FFMA-bound), and the
+    PSFNet fitting step (CUDA graph) against the same step in eager PyTorch on this GPU."""
+    import torch
+    import torch.nn as nn
+    import aadff_b200
+    from deeplens.psfnet import ThinLens
+    from deeplens.render_psf import render_psf, render_psf_map
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    hbm = 6531.6
+    for (N, H, W, ks) in [(4, 512, 512, 11), (16, 512, 512, 11), (16, 512, 512, 7), (1, 1080, 1920, 31)]:
+        tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=ks, sensor_size=[36.0, 24.0], sensor_res=(H, W)).to("cuda")
+        img = torch.rand(N, 3, H, W, device="cuda")
+        dep = -(300 + 5000 * torch.rand(N, 1, H, W, device="cuda"))
+        foc = -(500 + 3000 * torch.rand(N, device="cuda"))
+        ms = timeit(lambda: tl.render(img, dep, foc))
+        px = N * H * W
+        gbs = px * 28 / ms / 1e6
+        print(f"thinlens N{N} {H}x{W} k{ks}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  algorithmic 28 B/px -> {gbs:.0f} GB/s = "
+              f"{gbs / hbm:.3f} of measured HBM peak; {px * ks * ks * 4 / ms / 1e9:.2f} T tap-ops/s (per tap: ex2 + 3 FFMA + 3 LDS)", flush=True)
+    for (B, C, H, W, ks, grid) in [(4, 3, 512, 512, 11, 1), (4, 3, 512, 512, 11, 8), (1, 3, 1080, 1920, 31, 4)]:
+        img = torch.rand(B, C, H, W, device="cuda")
+        pm = torch.rand(C, grid * ks, grid * ks, device="cuda")
+        fn = (lambda: render_psf(img, pm)) if grid == 1 else (lambda: render_psf_map(img, pm, grid))
+        ms = timeit(fn)
+        fma = B * C * H * W * ks * ks
+        print(f"psf_conv B{B} {H}x{W} k{ks} grid{grid}: {ms:.3f} ms  {B * C * H * W / ms / 1e3:.1f} Mpix*ch/s  {fma / ms / 1e9:.2f} TFMA/s "
+              f"(fp32 FFMA peak 148 SM x 128 x 1.9 GHz = 36 TFMA/s)", flush=True)
+    # fitting step: bs = 128 as in the reference (psfnet.py:79)
+    ks, bs = 11, 128
+    lens = aadff_b200.PSFNet(kernel_size=ks, device="cuda")
+    lin = [m for m in lens.psfnet.net if isinstance(m, nn.Linear)]
+    tr = aadff_b200.native.NativeTrainer([l.weight.detach().cpu().numpy() for l in lin], [l.bias.detach().cpu().numpy() for l in lin], bs, 0)
+    inp = torch.rand(bs, 4, device="cuda")
+    tgt = torch.rand(bs, ks * ks, device="cuda")
+    tgt = tgt / tgt.sum(1, keepdim=True)
+    ms = timeit(lambda: aadff_b200.native.check(aadff_b200.native.lib.aadff_trainer_step(tr.handle, inp.data_ptr(), tgt.data_ptr(), 1e-4, None,
+                                                                                    torch.cuda.current_stream().cuda_stream)), iters=200)
+    mods = []
+    dims = [4, 64, 256] + [256] * 8 + [ks * ks]
+    for a, b in zip(dims[:-2], dims[1:-1]):
+        mods += [nn.Linear(a, b), nn.ReLU(inplace=True)]
+    net = nn.Sequential(*mods, nn.Linear(dims[-2], dims[-1]), nn.Sigmoid()).cuda()
+    opt = torch.optim.AdamW(net.parameters(), 1e-4)
+    def eager():
+        pred = torch.nn.functional.normalize(net(inp), p=1, dim=-1)
+        opt.zero_grad()
+        nn.MSELoss()(pred, tgt).backward()
+        opt.step()
+    ms_e = timeit(eager, iters=50)
+    print(f"train step bs={bs} k{ks}: CUDA-graph trainer {ms * 1e3:.1f} us/step, eager PyTorch (reference operators, same GPU) "
+          f"{ms_e * 1e3:.1f} us/step -> {ms_e / ms:.1f}x", flush=True)
+
+
 STAGES = {k[6:]: v for k, v in list(globals().items()) if k.startswith("stage_")}
 
 if __name__ == "__main__":

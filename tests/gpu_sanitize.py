@@ -31,3 +31,22 @@ for ks in (3, 7, 31):
     print("gather ragged ks", ks, float(aadff_b200.local_psf_render(img5, psf, ks).mean()))
 tl = aadff_b200.ThinLens(50.0, 1.8, 11, [36.0, 24.0], (24, 40)).to("cuda")
 print("thinlens", float(tl.render(img, dep, foc[:, 0]).mean()))
+# ---- round 2: tile-row ranges, PSF-map convolution, device-side sign flag, fitting step
+rows = lens.render_stack_rows(img, dep, foc, 1, 5, mode="parity")
+print("rows", tuple(rows.shape), float(rows.mean()))
+rows = lens.render_stack_rows(img, dep, foc, 0, 6, mode="fp32")
+print("rows fp32", tuple(rows.shape), float(rows.mean()))
+from deeplens.render_psf import render_psf, render_psf_map  # noqa: E402
+print("render_psf", float(render_psf(img5, torch.rand(5, 7, 7, device="cuda")).mean()))
+print("render_psf_map", float(render_psf_map(torch.rand(1, 3, 37, 41, device="cuda"), torch.rand(3, 15, 15, device="cuda"), 5).mean()))
+print("thinlens +depth", float(tl.render(img, -dep.clamp(max=-300.0), -foc[:, 0]).mean()))
+import torch.nn as nn  # noqa: E402
+lin = [m for m in lens.psfnet.net if isinstance(m, nn.Linear)]
+tr = aadff_b200.native.NativeTrainer([l.weight.detach().cpu().numpy() for l in lin], [l.bias.detach().cpu().numpy() for l in lin], 48, 0)
+x, t = torch.rand(48, 4, device="cuda"), torch.rand(48, 121, device="cuda")
+loss = torch.zeros(1, device="cuda")
+for _ in range(2):
+    aadff_b200.native.check(aadff_b200.native.lib.aadff_trainer_step(tr.handle, x.data_ptr(), t.data_ptr(), 1e-4, loss.data_ptr(), None))
+torch.cuda.synchronize()
+print("trainer loss", float(loss))
+tr.close()
