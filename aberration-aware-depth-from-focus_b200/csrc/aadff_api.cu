@@ -387,6 +387,7 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<true, false, 0>, attr, so));
 #define AADFF_SET_ATTR(U)                                                                        \
         CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, U>, attr, so));   \
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, U, true>, attr, so));   \
         CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, U>, attr, so));
         AADFF_SET_ATTR(0) AADFF_SET_ATTR(1) AADFF_SET_ATTR(3) AADFF_SET_ATTR(13) AADFF_SET_ATTR(12) AADFF_SET_ATTR(15)
 #undef AADFF_SET_ATTR
@@ -519,7 +520,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     // 32 KB stages (two packed K=32 slabs each) so that every issue iteration queues four MMAs
     P.kslab = (!any_lo && stages == 4) ? 2 : 1;
     P.n_stages = (P.kslab == 2) ? 4 : stages;
-    const int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
+    int grid = (int)std::min<long long>(P.n_tiles, h->num_sms);
     // kernel specialisation (fused_tc_kernel.cuh, template UNI): pattern 3 = all groups three-term (parity), 1 = all
     // single-term with the long ring (fast), 2 = econ, 5 = mixed, 0 = per-group terms at run time; +10 when the ring has
     // four stages and every group consumes a multiple of four of them (ring position of a K-step = compile-time)
@@ -538,7 +539,31 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     else if (all1 && P.kslab == 2) uni = 1;
     else if (econ_pat && aligned) uni = 12;
     else if (mixed_pat && aligned) uni = 15;
-    if (P.trace != nullptr && P.probes == nullptr) {
+    // 2-CTA clusters sharing the weight stream by multicast (fused_tc_kernel.cuh, CL2).  Built, bit-exact, and measured
+    // NOT to pay (profiles/NOTES_r02.md: -7 % at c2, +-1 % where power-capped), so it is off unless debug flag 8 asks for it.
+    const bool cl2 = P.probes == nullptr && P.trace == nullptr && uni != 0 && (P.dbg & 8u) && h->num_sms >= 2;
+    if (cl2) {
+        grid = (int)std::min<long long>((P.n_tiles + 1) & ~1ll, (long long)(h->num_sms & ~1));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TC_NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeClusterDimension;
+        la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+        cfg.attrs = la;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaSuccess;
+        switch (uni) {
+            case 1: le = cudaLaunchKernelEx(&cfg, fused_psfnet_render_kernel<false, false, 1, true>, P); break;
+            case 3: le = cudaLaunchKernelEx(&cfg, fused_psfnet_render_kernel<false, false, 3, true>, P); break;
+            case 13: le = cudaLaunchKernelEx(&cfg, fused_psfnet_render_kernel<false, false, 13, true>, P); break;
+            case 12: le = cudaLaunchKernelEx(&cfg, fused_psfnet_render_kernel<false, false, 12, true>, P); break;
+            default: le = cudaLaunchKernelEx(&cfg, fused_psfnet_render_kernel<false, false, 15, true>, P); break;
+        }
+        if (le != cudaSuccess) return fail(AADFF_E_CUDA, std::string("cluster launch: ") + cudaGetErrorString(le));
+    } else if (P.trace != nullptr && P.probes == nullptr) {
         fused_psfnet_render_kernel<true, false, 0><<<grid, TC_NT, smem, st>>>(P);
     } else {
 #define AADFF_LAUNCH(U)                                                                                   \
