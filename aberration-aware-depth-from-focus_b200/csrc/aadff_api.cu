@@ -78,6 +78,51 @@ bool launch_psf_conv(int ks, int grid, cudaStream_t st, const PsfConvArgs& a) {
     }
 }
 
+template <int KS>
+bool launch_thinlens(int ks, int grid, int smem, cudaStream_t st, const ThinLensArgs& a, const CUtensorMap& map) {
+    if constexpr (KS > 31) {
+        return false;
+    } else {
+        if (ks == KS) {
+            if (smem > 48 * 1024)      // per-device attribute
+                cudaFuncSetAttribute(thinlens_render_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            thinlens_render_kernel<KS><<<grid, TL_NT, smem, st>>>(a, map);
+            return true;
+        }
+        return launch_thinlens<KS + 2>(ks, grid, smem, st, a, map);
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [planes][H][W] fp32 image as a 3-D tensor map with a [box_c][box_h][box_w] box; false if TMA's rules are not met
+bool make_image_map(CUtensorMap* map, const float* img, long long planes, int H, int W, int box_w, int box_h, int box_c) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (W % 4) != 0 || (reinterpret_cast<uintptr_t>(img) % 16) != 0 || box_w > 256 || box_h > 256 || box_c > 256)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
@@ -838,21 +883,26 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
     CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     ThinLensArgs a{};
     a.img = img; a.depth = depth; a.foc = foc; a.out = out;
-    a.N = N; a.C = C; a.H = H; a.W = W; a.ks = ks;
+    a.N = N; a.C = C; a.H = H; a.W = W;
     a.k1 = (float)((double)foc_len / (double)fnum);
     a.foc_len = foc_len; a.ps = pixel_size; a.d_lo = d_lo; a.d_hi = d_hi; a.flip = flip_sign ? 1 : 0;
     a.flip_dev = flip_sign_dev;
-    const int HH = TL_TILE_H + ks - 1, pitch = (TL_TILE_W + ks - 1) | 1;
-    const int smem = TL_MAXC * HH * pitch * 4;
-    if (smem > optin) return fail(AADFF_E_UNSUPPORTED, "kernel size too large for the shared-memory halo tile");
-    if (smem > 48 * 1024)      // per-device attribute
-        CUDA_TRY(cudaFuncSetAttribute(thinlens_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (ks > 31) return fail(AADFF_E_UNSUPPORTED, "thin-lens kernel sizes above 31 are not built");
+    const int tl_r = (ks - 1) / 2, tl_sh = (4 - tl_r % 4) % 4;
+    const int HH = TL_TILE_H + ks - 1, BW = (TL_TILE_W + ks - 1 + tl_sh + 3) / 4 * 4;      // = ThinLensCfg<ks>::BW
     const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + TL_TILE_W - 1) / TL_TILE_W);
     const int grid = (int)std::min<long long>(tiles, (long long)sms * 4);
     for (int c0 = 0; c0 < C; c0 += TL_MAXC) {
         a.c0 = c0;
         a.cn = std::min(TL_MAXC, C - c0);
-        thinlens_render_kernel<<<grid, TL_TILE_H * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+        const int smem = (ks <= 15 ? 2 : 1) * ((a.cn * HH * BW + 31) / 32 * 32) * 4 + 128;      // = ThinLensCfg<ks>::SMEM_BYTES(cn)
+        if (smem > optin) return fail(AADFF_E_UNSUPPORTED, "kernel size too large for the shared-memory halo tile");
+        // the image halo of interior tiles arrives as one TMA box [cn][HH][BW] of the [N*C, H, W] tensor
+        CUtensorMap map;
+        std::memset(&map, 0, sizeof(map));
+        a.use_tma = make_image_map(&map, img, (long long)N * C, H, W, BW, HH, a.cn) && !(g_dbg_flags.load() & 16);
+        if (!launch_thinlens<1>(ks, grid, smem, static_cast<cudaStream_t>(stream), a, map))
+            return fail(AADFF_E_INVALID, "unsupported kernel size");
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }

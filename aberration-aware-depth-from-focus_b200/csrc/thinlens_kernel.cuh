@@ -4,30 +4,43 @@
 // -> normalise -> gather (deeplens/render_psf.py:76-107).  The reference materialises the
 // [N,H,W,k,k] PSF tensor through ~15 elementwise torch kernels; here taps live in registers.
 //
-// CTA tile = 8 rows x 32 columns, replicate-clamped image halo in shared memory, one thread
-// per pixel.  Bound by shared-memory reads / issue (3 LDS + ~9 ALU per tap), far above the
-// 28 B/pixel HBM traffic.
+// CTA tile = 8 rows x 32 columns, one thread per pixel, image halo tile in shared memory, planar per channel,
+// DOUBLE-BUFFERED: the halo of the next tile arrives under the current tile's arithmetic
+//   * as ONE TMA tensor-tile copy (cp.async.bulk.tensor.3d: box = [channels][rows][columns] of the [N*C, H, W] image,
+//     issued by one thread, completion on an mbarrier; the box starts at a 16-byte-aligned column) when the tile's halo
+//     lies inside the image, and
+//   * by per-thread cp.async of the replicate-clamped pixels (render_psf.py:96 pads with mode='replicate', which a
+//     TMA box cannot do: it zero-fills out-of-bounds elements) for tiles that touch the image border, or when the
+//     image does not meet TMA's 16-byte row-pitch rule (W % 4 != 0).
+// The Gaussian is separable: exp(-(dx^2+dy^2)/2s^2) = g(dx) g(dy), so a pixel needs (k+1)/2 + k exponentials instead of
+// k^2 (the first version was bound by two MUFU-class operations per tap: ex2 and an int->float conversion); the disk
+// mask (dx^2+dy^2 < radius^2) is an integer compare against a per-row limit.  Per tap that leaves
+// FMUL + ISETP/FSEL + FADD + 3 FFMA + 3 LDS.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include "ptx_sm100.cuh"
 
 namespace aadff {
 
 constexpr int TL_TILE_H = 8;
 constexpr int TL_TILE_W = 32;
 constexpr int TL_MAXC = 4;
+constexpr int TL_NT = TL_TILE_H * 32;
 
 struct ThinLensArgs {
     const float* img;     // [N,C,H,W]
     const float* depth;   // [N,H,W] mm (sign as given by the caller)
     const float* foc;     // [N] mm
     float* out;           // [N,C,H,W]
-    int N, C, H, W, ks, c0, cn;
+    int N, C, H, W, c0, cn;
     float k1;             // foc_len / fnum
     float foc_len, ps;    // focal length [mm], pixel size [mm]
     float d_lo, d_hi;     // depth clamp: 200, 20000 mm
     int flip;             // 1: depth and foc are negated first (reference: `if (depth < 0).any()`)
     const unsigned char* flip_dev;   // if not null, the decision is read from device memory (see any_negative_kernel):
                                      // the reference's data-dependent branch without a device->host round trip
+    int use_tma;          // the tensor map below is valid (W % 4 == 0, 16-byte aligned image)
 };
 
 // flag[0] |= any(x < 0)   (the reference's `if (depth < 0).any()`, psfnet.py:504, decided on the device)
@@ -38,26 +51,95 @@ __global__ void __launch_bounds__(256) any_negative_kernel(const float* __restri
     if (__syncthreads_or(neg) && threadIdx.x == 0) *flag = 1;     // benign race: every writer stores 1
 }
 
-__global__ void __launch_bounds__(TL_TILE_H * 32)
-thinlens_render_kernel(ThinLensArgs a) {
-    extern __shared__ float tl_img[];            // [cn][HH][pitch]
+// TMA: one [planes][rows][cols] box of a 3-D tensor map -> shared memory, completion counted on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+template <int KS>
+struct ThinLensCfg {
+    static constexpr int R = (KS - 1) / 2;
+    static constexpr int HH = TL_TILE_H + KS - 1;
+    static constexpr int HW = TL_TILE_W + KS - 1;
+    // TMA rules (measured: a box whose first element is not 16-byte aligned in global memory raises "illegal
+    // instruction"): the box starts SH columns left of the halo, at a multiple of 4 floats, and its width is a multiple of 4
+    static constexpr int SH = (4 - R % 4) % 4;
+    static constexpr int BW = (HW + SH + 3) / 4 * 4;     // box / smem row width
+    static constexpr int CSTRIDE = HH * BW;
+    __host__ __device__ static constexpr int BUF_FLOATS(int cn) { return (cn * CSTRIDE + 31) / 32 * 32; }   // 128-byte multiple: TMA destination alignment
+    // Two halo buffers (the next tile's copy runs under this tile's arithmetic) while they are small; large kernels keep
+    // one buffer: at k = 31 two 29 KB buffers left 3 CTAs per SM and the kernel, which lives on resident warps hiding
+    // LDS latency, lost 11 % (measured)
+    static constexpr int NBUF = KS <= 15 ? 2 : 1;
+    __host__ __device__ static constexpr int SMEM_BYTES(int cn) { return NBUF * BUF_FLOATS(cn) * 4 + 128; }  // barriers in front
+};
+
+template <int KS>
+__global__ void __launch_bounds__(TL_NT)
+thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap img_map) {
+    using Cfg = ThinLensCfg<KS>;
+    constexpr int R = Cfg::R, HH = Cfg::HH, HW = Cfg::HW, BW = Cfg::BW, SH = Cfg::SH, CSTRIDE = Cfg::CSTRIDE;
+    extern __shared__ __align__(128) unsigned char tl_smem[];
+    float* bufs = reinterpret_cast<float*>(tl_smem + 128);
+    const uint32_t bar0 = smem_u32(tl_smem);             // two mbarriers (one per buffer) in the first 16 bytes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ks = a.ks, r = (ks - 1) / 2;
-    const int HH = TL_TILE_H + ks - 1, HW = TL_TILE_W + ks - 1;
-    const int pitch = HW | 1;
-    const int cstride = HH * pitch;
     const int tiles_x = (a.W + TL_TILE_W - 1) / TL_TILE_W, tiles_y = (a.H + TL_TILE_H - 1) / TL_TILE_H;
     const long long n_tiles = (long long)a.N * tiles_x * tiles_y;
     const bool flip = a.flip_dev ? (*a.flip_dev != 0) : (a.flip != 0);
+    const int buf_floats = Cfg::BUF_FLOATS(a.cn);
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto coords = [&](long long tile, int& n, int& h0, int& w0) {
         const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
-        const int n = (int)(tile / ((long long)tiles_x * tiles_y));
-        const int h0 = ty * TL_TILE_H, w0 = tx * TL_TILE_W;
+        n = (int)(tile / ((long long)tiles_x * tiles_y));
+        h0 = ty * TL_TILE_H;
+        w0 = tx * TL_TILE_W;
+    };
+    auto interior = [&](int h0, int w0) {
+        return a.use_tma && h0 - R >= 0 && w0 - R >= 0 && h0 - R + HH <= a.H && w0 - R + HW <= a.W;
+    };
+    // start the halo copy of `tile` into buffer b
+    auto issue_halo = [&](long long tile, int b) {
+        int n, h0, w0;
+        coords(tile, n, h0, w0);
+        float* dst = bufs + b * buf_floats;
+        if (interior(h0, w0)) {
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(bar0 + 8 * b, (uint32_t)(a.cn * CSTRIDE * 4));
+                tma_load_3d(smem_u32(dst), &img_map, w0 - R - SH, h0 - R, n * a.C + a.c0, bar0 + 8 * b);
+            }
+        } else {
+            const uint32_t d0 = smem_u32(dst);
+            for (int idx = threadIdx.x; idx < a.cn * HH * HW; idx += TL_NT) {
+                const int c = idx / (HH * HW), rem = idx - c * (HH * HW);
+                const int yy = rem / HW, xx = rem - yy * HW;
+                const int gy = min(max(h0 + yy - R, 0), a.H - 1), gx = min(max(w0 + xx - R, 0), a.W - 1);   // replicate
+                cp_async4(d0 + 4u * (uint32_t)(c * CSTRIDE + yy * BW + xx + SH),
+                          a.img + ((long long)(n * a.C + a.c0 + c) * a.H + gy) * a.W + gx);
+            }
+        }
+    };
+
+    constexpr bool DB = Cfg::NBUF == 2;
+    uint32_t phase = 0;                       // bit b: parity to wait for on buffer b's mbarrier
+    int cur = 0;
+    if (DB && (long long)blockIdx.x < n_tiles) issue_halo(blockIdx.x, 0);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int n, h0, w0;
+        coords(tile, n, h0, w0);
         const int h = h0 + warp, w = w0 + lane;
         const bool ok = (h < a.H) && (w < a.W);
         // circle of confusion (ThinLens.coc, psfnet.py:503-511), operation order of the reference
-        float inv_2r2_log2e = 0.f, r2 = 0.f;
+        float cexp = 0.f, r2 = 0.f;
         if (ok) {
             float d = __ldg(a.depth + ((long long)n * a.H + h) * a.W + w);
             float f = __ldg(a.foc + n);
@@ -70,54 +152,53 @@ thinlens_render_kernel(ThinLensArgs a) {
             const float coc_px = fmaxf(__fdiv_rn(coc, a.ps), 0.1f);
             const float rad = coc_px * 0.5f;
             r2 = rad * rad;
-            inv_2r2_log2e = __fdiv_rn(-0.5f * 1.4426950408889634f, r2);    // exp(-d2/2/r2) = 2^(d2 * this)
+            cexp = __fdiv_rn(-0.5f * 1.4426950408889634f, r2);    // exp(-d2/2/r2) = 2^(d2 * cexp)
+        }
+        if (!DB) issue_halo(tile, 0);         // single buffer: released by the barrier that ended the previous tile
+        // this tile's halo has landed (TMA: mbarrier; cp.async: own copies + barrier below makes everyone's visible)
+        if (interior(h0, w0)) {
+            mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1);
+            phase ^= 1u << cur;
+        } else {
+            cp_async_wait_all();
         }
         __syncthreads();
-        {
-            const int total = a.cn * HH * HW;
-            for (int base = threadIdx.x; base < total; base += 4 * TL_TILE_H * 32) {
-                float v[4];
-                int slot[4];
+        if (DB && tile + gridDim.x < n_tiles) issue_halo(tile + gridDim.x, cur ^ 1);   // buffer cur^1 was released by the barrier that ended the previous tile
+
+        if (ok) {
+            // separable Gaussian: g[j] = 2^((j-R)^2 * cexp); the disk mask d2 < r2 as an integer compare (d2 is an integer)
+            float g[R + 1];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = base + u * TL_TILE_H * 32;
-                    slot[u] = -1;
-                    if (idx < total) {
-                        const int c = idx / (HH * HW), rem = idx - c * (HH * HW);
-                        const int yy = rem / HW, xx = rem - yy * HW;
-                        const int gy = min(max(h0 + yy - r, 0), a.H - 1), gx = min(max(w0 + xx - r, 0), a.W - 1);
-                        v[u] = __ldg(a.img + ((long long)(n * a.C + a.c0 + c) * a.H + gy) * a.W + gx);
-                        slot[u] = (c * HH + yy) * pitch + xx;
-                    }
+            for (int j = 0; j <= R; ++j) g[j] = exp2f((float)((j - R) * (j - R)) * cexp);
+            const int r2c = (r2 >= 4096.f) ? 4096 : (int)ceilf(r2);      // d2 <= 2 R^2 <= 450
+            float acc[TL_MAXC] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
+            const float* ib = bufs + cur * buf_floats + warp * BW + lane + SH;
+            const int cn = a.cn;
+#pragma unroll 1
+            for (int i = 0; i < KS; ++i) {
+                const int dy2 = (i - R) * (i - R);
+                const float gi = exp2f((float)dy2 * cexp);
+                const int lim = r2c - dy2;                     // tap (i, j) is inside the disk iff (j-R)^2 < lim
+                const float* prow = ib + i * BW;
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                    const int dx2 = (j - R) * (j - R);
+                    const float gj = g[j <= R ? j : KS - 1 - j];
+                    const float wt = (dx2 < lim) ? gi * gj : 0.f;   // psf_mask = (x^2 + y^2 < radius^2)
+                    wsum += wt;
+                    acc[0] = fmaf(prow[j], wt, acc[0]);
+                    if (cn > 1) acc[1] = fmaf(prow[j + CSTRIDE], wt, acc[1]);
+                    if (cn > 2) acc[2] = fmaf(prow[j + 2 * CSTRIDE], wt, acc[2]);
+                    if (cn > 3) acc[3] = fmaf(prow[j + 3 * CSTRIDE], wt, acc[3]);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (slot[u] >= 0) tl_img[slot[u]] = v[u];
             }
-        }
-        __syncthreads();
-        if (!ok) continue;
-        float acc[TL_MAXC] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
-        const float* ib = tl_img + warp * pitch + lane;
-        for (int i = 0; i < ks; ++i) {
-            const int dy2 = (i - r) * (i - r);
-            const float* prow = ib + i * pitch;
-#pragma unroll 4
-            for (int j = 0; j < ks; ++j) {
-                const float d2 = (float)(dy2 + (j - r) * (j - r));
-                float wt = exp2f(d2 * inv_2r2_log2e);
-                wt = (d2 < r2) ? wt : 0.f;                 // psf_mask = (x^2 + y^2 < radius^2)
-                wsum += wt;
-                acc[0] = fmaf(prow[j], wt, acc[0]);
-                if (a.cn > 1) acc[1] = fmaf(prow[j + cstride], wt, acc[1]);
-                if (a.cn > 2) acc[2] = fmaf(prow[j + 2 * cstride], wt, acc[2]);
-                if (a.cn > 3) acc[3] = fmaf(prow[j + 3 * cstride], wt, acc[3]);
-            }
-        }
-        const float inv = __fdiv_rn(1.0f, wsum);            // the centre tap always passes the mask: wsum >= 1
+            const float inv = __fdiv_rn(1.0f, wsum);            // the centre tap always passes the mask: wsum >= 1
 #pragma unroll
-        for (int c = 0; c < TL_MAXC; ++c)
-            if (c < a.cn) a.out[((long long)(n * a.C + a.c0 + c) * a.H + h) * a.W + w] = acc[c] * inv;
+            for (int c = 0; c < TL_MAXC; ++c)
+                if (c < a.cn) a.out[((long long)(n * a.C + a.c0 + c) * a.H + h) * a.W + w] = acc[c] * inv;
+        }
+        __syncthreads();                                        // everyone is done reading buffer `cur`
+        if (DB) cur ^= 1;
     }
 }
 

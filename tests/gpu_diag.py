@@ -340,10 +340,14 @@ def stage_rows2():
         dep = -(300 + 5000 * torch.rand(N, 1, H, W, device="cuda"))
         foc = -(500 + 3000 * torch.rand(N, device="cuda"))
         ms = timeit(lambda: tl.render(img, dep, foc))
+        aadff_b200.native.lib.aadff_debug_set_flags(16)
+        ms_no_tma = timeit(lambda: tl.render(img, dep, foc))
+        aadff_b200.native.lib.aadff_debug_set_flags(0)
+        print(f"  (halo by cp.async only, no TMA: {ms_no_tma:.3f} ms)")
         px = N * H * W
         gbs = px * 28 / ms / 1e6
         print(f"thinlens N{N} {H}x{W} k{ks}: {ms:.3f} ms  {px / ms / 1e3:.1f} Mpix/s  algorithmic 28 B/px -> {gbs:.0f} GB/s = "
-              f"{gbs / hbm:.3f} of measured HBM peak; {px * ks * ks * 4 / ms / 1e9:.2f} T tap-ops/s (per tap: ex2 + 3 FFMA + 3 LDS)", flush=True)
+              f"{gbs / hbm:.3f} of measured HBM peak; {px * ks * ks * 4 / ms / 1e9:.2f} T taps/s (per tap: FMUL + ISETP/FSEL + FADD + 3 FFMA + 3 LDS; issue-bound)", flush=True)
     for (B, C, H, W, ks, grid) in [(4, 3, 512, 512, 11, 1), (4, 3, 512, 512, 11, 8), (1, 3, 1080, 1920, 31, 4)]:
         img = torch.rand(B, C, H, W, device="cuda")
         pm = torch.rand(C, grid * ks, grid * ks, device="cuda")

@@ -557,6 +557,21 @@ def test_thinlens_sign_decided_on_device_and_focus_sentinel(pkg):
     neg = tl.render(img, -dep, -foc)
     assert torch.equal(pos, neg)
     assert maxabs(pos, orc.thinlens_render(img.cpu(), dep.cpu(), foc.cpu(), 11, 50.0, 1.8, tl.ps)) < 5e-6
+    # interior tiles take their halo as one TMA tensor tile, border tiles (and W % 4 != 0 images) by clamped cp.async:
+    # both against the oracle, and the TMA path bit-equal to the all-cp.async path (debug flag 16)
+    for (N, C, H, W, ks) in [(2, 3, 72, 200, 11), (1, 4, 40, 136, 7), (1, 3, 64, 130, 11), (1, 1, 96, 160, 31), (1, 5, 33, 68, 3)]:
+        tlk = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=ks, sensor_size=[36.0, 24.0], sensor_res=(H, W)).to("cuda")
+        im = torch.rand(N, C, H, W, generator=gen)
+        dp = 300 + 6000 * torch.rand(N, 1, H, W, generator=gen)
+        fc = 500 + 3000 * torch.rand(N, generator=gen)
+        ref = orc.thinlens_render(im, dp, fc, ks, 50.0, 1.8, tlk.ps)
+        got = tlk.render(im.cuda(), dp.cuda(), fc.cuda())
+        assert maxabs(got, ref) < 5e-6, (N, C, H, W, ks)
+        pkg.native.lib.aadff_debug_set_flags(16)
+        try:
+            assert torch.equal(tlk.render(im.cuda(), dp.cuda(), fc.cuda()), got)
+        finally:
+            pkg.native.lib.aadff_debug_set_flags(0)
     graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
