@@ -32,7 +32,8 @@ from aadff_render import local_psf_render                        # noqa: E402
 from aadff_factory import get_lens, get_dataset                  # noqa: E402
 from aadff_focus import select_focus_dist                        # noqa: E402
 from aadff_install import install, uninstall                     # noqa: E402
+from aadff_data import preprocess_rgbd                           # noqa: E402
 import sharding                                                  # noqa: E402
 
 __all__ = ["native", "sharding", "PSFNet", "ThinLens", "local_psf_render", "get_lens", "get_dataset",
-           "select_focus_dist", "install", "uninstall", "DMIN", "DMAX"]
+           "select_focus_dist", "install", "uninstall", "preprocess_rgbd", "DMIN", "DMAX"]

@@ -20,6 +20,7 @@
 #include "focus_kernel.cuh"
 #include "psf_conv_kernel.cuh"
 #include "train_kernels.cuh"
+#include "preprocess_kernel.cuh"
 #include "econ_calib.h"
 
 using namespace aadff;
@@ -935,6 +936,25 @@ int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out,
                             ((a.max_cw + PC_TILE_W - 1) / PC_TILE_W);
     const int nblk = (int)std::min<long long>(tiles, (long long)sms * 8);
     if (!launch_psf_conv<1>(ks, nblk, static_cast<cudaStream_t>(stream), a)) return fail(AADFF_E_INVALID, "unsupported kernel size");
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* aif_out, float* depth_out, int B, int H, int W,
+                             int h, int w, float depth_div, int depth_mode, const float* jitter, const uint8_t* flips,
+                             void* stream) {
+    if ((!bgr && !depth) || (bgr && !aif_out) || (depth && !depth_out)) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || H < 1 || W < 1 || h < 1 || w < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (depth && !(depth_div > 0.f)) return fail(AADFF_E_INVALID, "depth divisor must be positive");
+    if (depth_mode != 0 && depth_mode != 1) return fail(AADFF_E_INVALID, "depth_mode must be 0 (antialias) or 1 (cv2 linear)");
+    if (B == 0) return AADFF_OK;
+    PreprocessArgs a{};
+    a.bgr = bgr; a.depth = depth; a.aif_out = aif_out; a.depth_out = depth_out; a.jitter = jitter; a.flips = flips;
+    a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.depth_div = depth_div; a.depth_mode = depth_mode;
+    const long long total = (long long)B * h * w;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;

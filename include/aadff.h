@@ -116,6 +116,17 @@ int aadff_any_negative_f32(const float* x, int64_t n, unsigned char* flag_dev, v
 int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out, int B, int C, int H, int W, int ks,
                              int grid, const int* row_bounds, const int* col_bounds, void* stream);
 
+/* Replaces the per-sample CPU work of the reference's Dataset classes after file decoding (dff/dataset.py:43-52
+ * Matterport3D, :190-205 Middlebury; AutoAgument's colour jitter and flips :259-272): BGR uint8 -> RGB float / 255
+ * (-> clip(0.5 + contrast*(x-0.5) + brightness, 0, 1) -> flips) -> torchvision Resize((h,w), antialias=True), and
+ * uint16 depth / depth_div (-> flips) -> the same resize (depth_mode 0) or cv2.resize INTER_LINEAR (depth_mode 1).
+ *   bgr [B,H,W,3] uint8, depth [B,H,W] uint16 (either may be NULL), aif_out [B,3,h,w], depth_out [B,1,h,w] fp32;
+ *   jitter [B,2] = (contrast, brightness) per image, contrast < 0 = no jitter, or NULL; flips [B]: bit 0 horizontal,
+ *   bit 1 vertical, or NULL.  Device pointers, stream-ordered.  AutoAgument's spline rotation is not rebuilt.       */
+int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* aif_out, float* depth_out, int B, int H, int W,
+                             int h, int w, float depth_div, int depth_mode, const float* jitter, const uint8_t* flips,
+                             void* stream);
+
 /* Replaces select_focus_dist(depth, num, mode='linear') (dff/utils.py:4-51), the producer of foc_dist in the
  * training loop: per image the minimum over valid (> 0) depths and the maximum depth, then `num` (> 3) focus
  * distances linearly between them, ascending.  depth_m [B, HW] (metres, any unit really), out [B, num]; device.

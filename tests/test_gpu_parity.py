@@ -363,6 +363,38 @@ def test_train_psfnet_matches_torch_autograd(pkg):
     assert any(not torch.equal(a, b) for a, b in zip(before, lens.psfnet.parameters()))
 
 
+def test_dataset_preparation_matches_reference_datasets(pkg):
+    """f4 row, host data path: ToTensor + BGR->RGB + /255 + AutoAgument jitter/flips + Resize(antialias=True) (and
+    cv.resize for Middlebury's depth) on the device, against what the reference's own Dataset classes returned for
+    the same decoded arrays (tests/golden/make_golden_f4_data.py ran dff/dataset.py: Matterport3D, Middlebury)."""
+    g = load_golden("kat_j_dataset_prep.npz")
+    bgr = T(g["mp_bgr"]).cuda()[None]
+    dep = torch.from_numpy(g["mp_depth"].astype(np.int16)).view(torch.uint16).cuda()[None]
+    for tag in "abc":                                   # down-scale by 2, non-integer factor, identity
+        aif, d = pkg.preprocess_rgbd(bgr, dep, tuple(int(v) for v in g[f"mp_{tag}_size"]), depth_div=4000.0)
+        assert aif.shape[1:] == g[f"mp_{tag}_aif"].shape and maxabs(aif[0], T(g[f"mp_{tag}_aif"])) < 2e-6, tag
+        assert maxabs(d[0], T(g[f"mp_{tag}_depth"])) < 2e-6, tag
+    aif, d = pkg.preprocess_rgbd(bgr, dep, (48, 65), depth_div=4000.0, jitter=T(g["mp_aug_jitter"])[None],
+                                 flips=torch.tensor([int(g["mp_aug_flips"])], dtype=torch.uint8))
+    assert maxabs(aif[0], T(g["mp_aug_aif"])) < 2e-6 and maxabs(d[0], T(g["mp_aug_depth"])) < 2e-6
+    mb_dep = torch.from_numpy(g["mb_depth"].astype(np.int16)).view(torch.uint16).cuda()[None]
+    aif, d = pkg.preprocess_rgbd(T(g["mb_bgr"]).cuda()[None], mb_dep, (48, 64), depth_div=1000.0, depth_mode="cv2")
+    assert maxabs(aif[0], T(g["mb_aif"])) < 2e-6 and maxabs(d[0], T(g["mb_depth_out"])) < 5e-6
+    # a batch: per-image jitter / flips, image-only and depth-only calls
+    b2 = torch.cat([bgr, bgr.flip(1)]), torch.cat([dep, dep.flip(1)])
+    aif2, d2 = pkg.preprocess_rgbd(b2[0], b2[1], (48, 65), jitter=torch.tensor([[-1.0, 0.0], [-1.0, 0.0]]),
+                                   flips=torch.tensor([0, 2], dtype=torch.uint8))
+    assert torch.equal(aif2[0], aif2[1]) and torch.equal(d2[0], d2[1])          # flipping a flipped image = the image
+    only_img, none_d = pkg.preprocess_rgbd(bgr, None, (48, 65))
+    assert none_d is None and maxabs(only_img[0], T(g["mp_a_aif"])) < 2e-6
+    # straight into the simulator: decoded arrays -> focal stack without touching the host
+    lens = pkg.PSFNet(kernel_size=11, device="cuda")
+    lens.load_net(CKPT)
+    a, dm = pkg.preprocess_rgbd(bgr, dep, (48, 64), depth_div=1000.0)
+    stack, foc = lens.simulate_focal_stack(a, dm, 5)
+    assert stack.shape == (1, 3, 5, 48, 64) and bool(torch.isfinite(stack).all())
+
+
 # --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
 @pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 3, 9, 1), (1, 3, 1, 21), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17),
                                      (2, 3, 7, 130)])
