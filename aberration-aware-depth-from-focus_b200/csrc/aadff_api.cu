@@ -13,6 +13,7 @@
 
 #include "../../include/aadff.h"
 #include "fused_tc_kernel.cuh"
+#include "fused_fast2_kernel.cuh"
 #include "gather_kernel.cuh"
 #include "gather_coalesced_kernel.cuh"
 #include "mlp_fp32_kernel.cuh"
@@ -496,6 +497,53 @@ static int ensure_econ(aadff_psfnet_t h) {
     return AADFF_OK;
 }
 
+// AADFF_MODE_FAST with two tiles in flight per CTA (fused_fast2_kernel.cuh).  Built, bit-identical to the one-tile kernel
+// and measured SLOWER (0.80-0.91x, profiles/NOTES_r02.md: the second tile's activations leave a 64 KB weight ring, too
+// shallow to cover the L2 latency at fast mode's 64 B/clk per SM), so it only runs when debug flag 32 asks for it.
+// Returns 1 if the launch does not qualify (flag not set, several head blocks, shared-memory budget).
+static int launch_fast2(aadff_psfnet_t h, const RenderArgs& ra, cudaStream_t st, long long tile_row0, long long tile_row1) {
+    if (!h->tc_ok || h->n_groups != h->n_hidden + 1 || !(g_dbg_flags.load() & 32)) return 1;
+    F2Params P{};
+    P.ra = ra;
+    P.wpack = h->d_wpack;
+    P.bias = h->d_bias_tc;
+    P.w0b0 = h->d_w0b0;
+    P.n_groups = h->n_groups;
+    P.n_hidden = h->n_hidden;
+    P.n_bias = h->n_bias;
+    P.bias_skip = h->head_bias0;
+    P.kk = h->kk;
+    for (int i = 0; i < h->n_groups; ++i) { P.g[i] = h->groups[i]; P.g[i].terms = 1; }
+    P.tiles_x = (ra.W + TC_TILE_W - 1) / TC_TILE_W;
+    P.tiles_y = (ra.H + TC_TILE_H - 1) / TC_TILE_H;
+    P.n_tiles = (long long)P.tiles_x * P.tiles_y * ra.N * ra.S;
+    if (tile_row1 >= 0) {
+        P.tile0 = tile_row0 * P.tiles_x;
+        P.n_tiles = (tile_row1 - tile_row0) * P.tiles_x;
+        if (P.n_tiles <= 0) return AADFF_OK;
+    }
+    P.halo_pitch = TC_TILE_W + ra.ks - 1;
+    P.halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * P.halo_pitch * 16;
+    const uint32_t bias_bytes = (uint32_t)(h->n_bias - h->head_bias0) * 4;
+    P.off_stage = 2 * TC_A_PART_BYTES;
+    P.off_bias = P.off_stage + F2_STAGES * TC_STAGE_BYTES;
+    P.off_w0 = P.off_bias + bias_bytes;
+    P.off_halo = (P.off_w0 + 320 * 4 + 15u) & ~15u;
+    P.off_red = P.off_halo + 2 * P.halo_bytes;
+    P.off_bar = P.off_red + 2 * TC_M * 5 * 4;
+    P.off_ones = (P.off_bar + TC_BAR_BYTES + 15u) & ~15u;
+    P.off_bslab = P.off_ones + 2 * TC_A_LBO;
+    const uint32_t smem = P.off_bslab + 2 * TC_BSLAB_BYTES;
+    if (smem > (uint32_t)h->smem_optin) return 1;
+    const long long units = (P.n_tiles + 1) / 2;
+    const int grid = (int)std::min<long long>(units, h->num_sms);
+    cudaFuncSetAttribute(fused_fast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin);
+    fused_fast2_kernel<<<grid, TC_NT, smem, st>>>(P);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
 static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st, long long tile_row0 = 0,
                      long long tile_row1 = -1, const float* probes = nullptr, float* psf_out = nullptr,
                      long long n_probes = 0) {
@@ -503,6 +551,10 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     if (mode == AADFF_MODE_ECON) {
         const int rc = ensure_econ(h);
         if (rc) return rc;
+    }
+    if (mode == AADFF_MODE_FAST && probes == nullptr && g_trace.load() == nullptr) {
+        const int rc = launch_fast2(h, ra, st, tile_row0, tile_row1);
+        if (rc <= 0) return rc;                                   // launched (0) or failed (< 0); 1 = not eligible
     }
     TcParams P{};
     P.ra = ra;

@@ -31,16 +31,37 @@ train_gemm_kernel(const float* __restrict__ A, long long sa_i, long long sa_k, c
     const int i0 = blockIdx.y * TG_TILE, j0 = blockIdx.x * TG_TILE;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;           // 16 x 16 threads, 2 x 2 outputs each
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    for (int k0 = 0; k0 < K; k0 += TG_K) {
-        for (int e = threadIdx.x; e < TG_K * TG_TILE; e += TG_NT) {
-            // choose the fast-running index along the contiguous direction of each operand
+    constexpr int PER = TG_K * TG_TILE / TG_NT;                       // operand elements per thread and K tile (4)
+    // the K tile after the current one is fetched into registers while the current one is multiplied: these GEMMs are
+    // a dependent chain of small launches, so the global-load latency per K tile is what they cost
+    float pa[PER], pb[PER];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int e = threadIdx.x + r * TG_NT;
+            int ka, ia, kb, jb;               // the fast-running index follows the contiguous direction of each operand
+            if (sa_k == 1) { ka = e % TG_K; ia = e / TG_K; } else { ia = e % TG_TILE; ka = e / TG_TILE; }
+            if (sb_j == 1) { jb = e % TG_TILE; kb = e / TG_TILE; } else { kb = e % TG_K; jb = e / TG_K; }
+            pa[r] = (i0 + ia < M && k0 + ka < K) ? __ldg(A + (i0 + ia) * sa_i + (k0 + ka) * sa_k) : 0.f;
+            pb[r] = (j0 + jb < N && k0 + kb < K) ? __ldg(B + (k0 + kb) * sb_k + (j0 + jb) * sb_j) : 0.f;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int e = threadIdx.x + r * TG_NT;
             int ka, ia, kb, jb;
             if (sa_k == 1) { ka = e % TG_K; ia = e / TG_K; } else { ia = e % TG_TILE; ka = e / TG_TILE; }
             if (sb_j == 1) { jb = e % TG_TILE; kb = e / TG_TILE; } else { kb = e % TG_K; jb = e / TG_K; }
-            sA[ka][ia] = (i0 + ia < M && k0 + ka < K) ? __ldg(A + (i0 + ia) * sa_i + (k0 + ka) * sa_k) : 0.f;
-            sB[kb][jb] = (j0 + jb < N && k0 + kb < K) ? __ldg(B + (k0 + kb) * sb_k + (j0 + jb) * sb_j) : 0.f;
+            sA[ka][ia] = pa[r];
+            sB[kb][jb] = pb[r];
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += TG_K) {
+        stash();
         __syncthreads();
+        if (k0 + TG_K < K) fetch(k0 + TG_K);
 #pragma unroll
         for (int k = 0; k < TG_K; ++k) {
             const float a0 = sA[k][ty], a1 = sA[k][ty + 16], b0 = sB[k][tx], b1 = sB[k][tx + 16];

@@ -165,7 +165,9 @@ int aadff_debug_set_desc_swap(int swap);
 int aadff_debug_set_trace(void* device_buffer);
 int aadff_debug_trace_entries(void);
 /* Debug switches, 0 restores normal operation.  What-if timing of the fused kernel (results become invalid):
- * bit 0 = skip the weight copies, bit 1 = skip the operand stores.  16 = aadff_thinlens_render_f32 fetches every halo tile with
+ * bit 0 = skip the weight copies, bit 1 = skip the operand stores.  32 = AADFF_MODE_FAST through the two-tiles-in-flight kernel
+ * (fused_fast2_kernel.cuh; same results, measured slower -- profiles/NOTES_r02.md).
+ * 16 = aadff_thinlens_render_f32 fetches every halo tile with
  * clamped cp.async instead of TMA tensor tiles for interior tiles (results unchanged).  8 = run the fused kernel as 2-CTA clusters that share
  * the weight stream through multicast bulk copies (results unchanged; measured not to pay, see profiles/NOTES_r02.md).  Cross-check paths (results stay valid):
  * 128 = aadff_local_psf_render_f32 through the older cp.async.bulk streaming kernel instead of the register-

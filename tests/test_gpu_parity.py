@@ -7,7 +7,7 @@ Tolerances (max-abs on [0,1] images, fp32):
   parity mode (tcgen05, fp16 hi/lo split, 3 terms)   1e-4   -- north_star's bar; observed <= 1e-5, tested at 2e-5
   fp32 mode   (CUDA cores)                           5e-6
   mixed mode                                         1e-3
-  fast mode   (single fp16 term)                     3e-2 max, 3e-4 mean  (stated tolerance of that mode)
+  fast mode   (single fp16 term)                     2e-2 max, 1e-4 mean  (stated tolerance of that mode; observed <= 1.4e-2 on noise images / 6e-5 mean)
 """
 import ctypes
 import os
@@ -23,8 +23,15 @@ pytestmark = pytest.mark.gpu
 
 # north_star bar: 1e-4.  parity is tested at 2e-5 (observed <= 1e-5) and econ at 6e-5 (observed <= 3.4e-5 with the
 # calibrated fp16 weights; plain rounding gave 6e-5 .. 9e-5) so that a regression shows before the bar is reached.
-TOL = {"parity": 2e-5, "econ": 6e-5, "fp32": 5e-6, "mixed": 1e-3, "fast": 3e-2}
+TOL = {"parity": 2e-5, "econ": 6e-5, "fp32": 5e-6, "mixed": 1e-3, "fast": 2e-2}
 CKPT = os.path.join(GOLDEN, "rf50mm_PSFNet480x640_ks11.pkl")
+BASELINE_TOL = {"parity": 2e-5, "econ": 6e-5, "fp32": 5e-6, "fast": 2e-2}        # fast: + mean-abs < 1e-4
+
+
+def _report(tag, mode, err):
+    print(f"[parity-at-size] {tag:28s} mode={mode:7s} max-abs vs reference = {err:.3e}")
+
+
 
 
 def T(a):
@@ -174,6 +181,28 @@ def test_render_kat_b_full_frame(lens, mode):
     assert abs(float(out.double().sum()) - float(g["sum"])) < 1.0
 
 
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+def test_warm_up_script_body_vs_reference_cpu_output(pkg, mode):
+    """The body of 0_warm_up.py (lines 9-22, BASELINE config c1) through the shadow package, on the resolution chart
+    + the real Adirondack depth map, against what the reference itself produced on the CPU
+    (tests/golden/make_golden_warmup.py).  885 pixels of that depth map are invalid (0) -> z clamps."""
+    from deeplens.psfnet import PSFNet                                    # 0_warm_up.py:3
+    g = load_golden("kat_k_warmup_c1.npz")
+    psfnet = PSFNet(filename='./lenses/rf50mm/lens.json', sensor_res=(480, 640), kernel_size=11, mode=mode)
+    psfnet.load_net(CKPT)
+    psfnet.analysis()
+    img = torch.tensor(g["img_u8"]).permute(2, 0, 1).unsqueeze(0).float() / 255
+    depth = torch.tensor(g["depth_m"]).unsqueeze(0).unsqueeze(0).float()
+    depth = - depth * 1e3
+    focus_dist = torch.tensor([-2400.])
+    out = psfnet.render(img.to(psfnet.device), depth.to(psfnet.device), focus_dist.to(psfnet.device)).cpu()
+    err = max(float((out[..., ::3, ::3] - T(g["out_sub"])).abs().max()),
+              float((out[..., [0, 240, 479], :] - T(g["out_rows"])).abs().max()))
+    _report("c1 0_warm_up.py body", mode, err)
+    assert out.shape == (1, 3, 480, 640) and err < BASELINE_TOL[mode]
+    assert abs(float(out.double().sum()) - float(g["sum"])) < 921600 * 1e-6
+
+
 def test_econ_calibration_beats_plain_rounding(pkg, lens):
     """econ mode (2 terms for L5.. and the head) on a noise image at BASELINE c2 size, against the fp32 CUDA-core kernel:
     the calibrated weights (csrc/econ_calib.h) stay under 6e-5; plain fp16 rounding (debug flag 256) is >1.5x worse."""
@@ -215,7 +244,7 @@ def test_stack_golden_ragged(lens, mode):
     d = (out.cpu() - T(g["out"])).abs()
     assert float(d.max()) < TOL[mode]
     if mode == "fast":
-        assert float(d.mean()) < 3e-4
+        assert float(d.mean()) < 1e-4
     # the reference's own loop: one render per slice, stacked on dim 2 -- bit-identical
     loop = torch.stack([lens.render(img, -dm * 1e3, -foc_m[:, s] * 1e3, mode=mode) for s in range(5)], dim=2)
     assert torch.equal(loop, out)
@@ -475,14 +504,7 @@ def test_c2_constant_image_is_fixed_point(lens):
 # --------------------------------------------------------------------------- BASELINE sizes against the REFERENCE's output
 # (tests/golden/make_golden_baseline_sizes.py ran the reference itself on bench.py's seeded workloads; the inputs are
 #  regenerated here from the same seed).  max-abs is printed (pytest -s / the GPU log) and asserted per mode.
-BASELINE_TOL = {"parity": 2e-5, "econ": 6e-5, "fp32": 5e-6}
-
-
-def _report(tag, mode, err):
-    print(f"[parity-at-size] {tag:28s} mode={mode:7s} max-abs vs reference = {err:.3e}")
-
-
-@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32", "fast"])
 def test_c2_full_size_vs_reference_golden(lens, mode):
     """BASELINE config c2 (1 x 5 x 512 x 512, k = 11), all five slices, vs the reference's PSFNet.render."""
     g = load_golden("kat_c2_1x5x512x512.npz")
@@ -494,10 +516,15 @@ def test_c2_full_size_vs_reference_golden(lens, mode):
               float((out[..., [0, 1, 255, 256, 510, 511], :] - T(g["out_rows"])).abs().max()))
     _report("c2 1x5x512x512 k=11", mode, err)
     assert err < BASELINE_TOL[mode]
+    if mode == "fast":
+        mean = float((out[..., ::4, ::4] - T(g["out_sub"])).abs().mean())
+        print(f"[parity-at-size] c2 fast mean-abs = {mean:.3e}")
+        assert mean < 1e-4
+        return
     assert float((out.double().sum((1, 3, 4)) - T(g["sums"])).abs().max()) < 786432 * (1e-6 if mode == "econ" else 5e-7)   # mean bias over ALL pixels of a slice
 
 
-@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+@pytest.mark.parametrize("mode", ["parity", "econ", "fp32", "fast"])
 def test_c3_full_size_vs_reference_golden(lens, mode):
     """BASELINE config c3 (16 x 5 x 256 x 256, k = 11): all 16 images, all slices (1/64 of the pixels of every slice,
     1/4 of image 3, sums over everything); fp32 on images 0..3 only (16.5 Mpix/s kernel)."""
@@ -511,6 +538,9 @@ def test_c3_full_size_vs_reference_golden(lens, mode):
               float((out[3, :, :, ::2, ::2] - T(g["out_full_img3"])).abs().max()))
     _report("c3 16x5x256x256 k=11", mode, err)
     assert err < BASELINE_TOL[mode]
+    if mode == "fast":
+        assert float((out[..., ::8, ::8] - T(g["out_sub"])[:n]).abs().mean()) < 1e-4
+        return
     assert float((out.double().sum((1, 3, 4)) - T(g["sums"])[:n]).abs().max()) < 196608 * (1e-6 if mode == "econ" else 5e-7)
 
 
@@ -547,6 +577,30 @@ def test_c4_full_size_vs_reference_golden(lens31_bench, mode):
     _report("c4 1x10x1080x1920 k=31", mode, err)
     # seeded random weights (no k=31 checkpoint exists): econ's calibration is certified at the north_star bar there
     assert err < (1e-4 if mode == "econ" else BASELINE_TOL[mode])
+
+
+def test_fast_mode_two_tiles_in_flight_equals_one_tile_kernel(pkg, lens):
+    """The two-tiles-in-flight variant of AADFF_MODE_FAST (fused_fast2_kernel.cuh, debug flag 32; measured slower than
+    the one-tile kernel and therefore not the default) evaluates the same single-term arithmetic in the same order:
+    bit-identical stacks, ragged shapes, odd tile counts (a dummy second tile), tile-row ranges, C = 1 / 4."""
+    sh = pkg.sharding
+    for (N, C, S, H, W) in [(1, 3, 1, 8, 16), (1, 3, 3, 37, 50), (2, 4, 2, 24, 40), (1, 1, 5, 64, 96), (3, 3, 4, 40, 56)]:
+        gen = torch.Generator().manual_seed(H + W)
+        img = torch.rand(N, C, H, W, generator=gen).cuda()
+        _, dm = orc.synthetic_rgbd(N, H, W, seed=H)
+        foc = -orc.synthetic_focus(dm, S).cuda() * 1e3
+        dep = -dm.cuda() * 1e3
+        one = lens.render_stack(img, dep, foc, mode="fast")
+        R0, R1 = sh.tile_row_range(N, S, H, 3, 1)
+        one_rows = lens.render_stack_rows(img, dep, foc, R0, R1, mode="fast")
+        pkg.native.lib.aadff_debug_set_flags(32)
+        try:
+            two = lens.render_stack(img, dep, foc, mode="fast")
+            two_rows = lens.render_stack_rows(img, dep, foc, R0, R1, mode="fast")
+        finally:
+            pkg.native.lib.aadff_debug_set_flags(0)
+        assert torch.equal(two, one) and torch.equal(two_rows, one_rows), (N, C, S, H, W)
+        assert maxabs(two, lens.render_stack(img, dep, foc, mode="parity")) < TOL["fast"]
 
 
 def test_tile_row_ranges_are_bit_identical_to_the_full_launch(pkg, lens):
