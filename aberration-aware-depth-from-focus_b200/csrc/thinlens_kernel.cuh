@@ -25,7 +25,7 @@ namespace aadff {
 
 constexpr int TL_TILE_H = 8;
 constexpr int TL_TILE_W = 32;
-constexpr int TL_MAXC = 4;
+constexpr int TL_MAXC = 3;                // channels per launch (RGB); more channels = more passes
 constexpr int TL_NT = TL_TILE_H * 32;
 
 struct ThinLensArgs {
@@ -171,15 +171,19 @@ thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap
 #pragma unroll
             for (int j = 0; j <= R; ++j) g[j] = exp2f((float)((j - R) * (j - R)) * cexp);
             const int r2c = (r2 >= 4096.f) ? 4096 : (int)ceilf(r2);      // d2 <= 2 R^2 <= 450
-            float acc[TL_MAXC] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.f;
+            float acc[TL_MAXC] = {0.f, 0.f, 0.f}, wsum = 0.f;
             const float* ib = bufs + cur * buf_floats + warp * BW + lane + SH;
-            const int cn = a.cn;
+            // absent channels re-read channel 0 (results discarded at the store): unconditional loads keep the tap loop
+            // free of branches (`if (cn > 1) ... prow[j + CSTRIDE]` compiled to a branch per tap and channel)
+            const int cs1 = a.cn > 1 ? CSTRIDE : 0, cs2 = a.cn > 2 ? 2 * CSTRIDE : 0;
 #pragma unroll 1
             for (int i = 0; i < KS; ++i) {
                 const int dy2 = (i - R) * (i - R);
                 const float gi = exp2f((float)dy2 * cexp);
                 const int lim = r2c - dy2;                     // tap (i, j) is inside the disk iff (j-R)^2 < lim
                 const float* prow = ib + i * BW;
+                const float* prow1 = prow + cs1;
+                const float* prow2 = prow + cs2;
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
                     const int dx2 = (j - R) * (j - R);
@@ -187,9 +191,8 @@ thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap
                     const float wt = (dx2 < lim) ? gi * gj : 0.f;   // psf_mask = (x^2 + y^2 < radius^2)
                     wsum += wt;
                     acc[0] = fmaf(prow[j], wt, acc[0]);
-                    if (cn > 1) acc[1] = fmaf(prow[j + CSTRIDE], wt, acc[1]);
-                    if (cn > 2) acc[2] = fmaf(prow[j + 2 * CSTRIDE], wt, acc[2]);
-                    if (cn > 3) acc[3] = fmaf(prow[j + 3 * CSTRIDE], wt, acc[3]);
+                    acc[1] = fmaf(prow1[j], wt, acc[1]);
+                    acc[2] = fmaf(prow2[j], wt, acc[2]);
                 }
             }
             const float inv = __fdiv_rn(1.0f, wsum);            // the centre tap always passes the mask: wsum >= 1
