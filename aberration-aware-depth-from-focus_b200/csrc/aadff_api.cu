@@ -1004,8 +1004,9 @@ int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* a
     PreprocessArgs a{};
     a.bgr = bgr; a.depth = depth; a.aif_out = aif_out; a.depth_out = depth_out; a.jitter = jitter; a.flips = flips;
     a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.depth_div = depth_div; a.depth_mode = depth_mode;
-    const long long total = (long long)B * h * w;
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    const long long per_image = (long long)h * w;
+    const dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 148 * 16), (unsigned)B);
+    if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
     preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());

@@ -44,10 +44,25 @@ __device__ __forceinline__ float aa_weight(int j, int lo, float center, float in
     return fmaxf(0.f, 1.f - fabsf(((float)(j + lo) - center + 0.5f) * invscale));
 }
 
+constexpr int PP_MAXW = 12;      // filter taps per axis kept in registers (down-scaling factors up to ~5.5); beyond: recomputed
+
+// grid = (chunks of output pixels, image): a block works on ONE image, so the whole per-value arithmetic of the image --
+// /255 and the colour jitter, both evaluated in double like the reference's numpy code and then rounded to fp32 as its
+// astype('float32') does -- is a 256-entry table in shared memory: per tap and channel one byte load, one LDS, one FFMA.
 __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessArgs a) {
-    const long long total = (long long)a.B * a.h * a.w;
+    __shared__ float lut[256];
+    const int b = blockIdx.y;
+    {
+        double con = -1.0, bri = 0.0;
+        if (a.jitter) { con = (double)a.jitter[2 * b]; bri = (double)a.jitter[2 * b + 1]; }
+        double v = (double)threadIdx.x / 255.0;
+        if (con >= 0.0) v = fmin(fmax(0.5 + con * (v - 0.5) + bri, 0.0), 1.0);
+        lut[threadIdx.x] = (float)v;
+    }
+    __syncthreads();
+    const long long total = (long long)a.h * a.w;
     for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(id % a.w), oy = (int)((id / a.w) % a.h), b = (int)(id / ((long long)a.w * a.h));
+        const int ox = (int)(id % a.w), oy = (int)(id / a.w);
         const int fl = a.flips ? a.flips[b] : 0;
         const bool flx = fl & 1, fly = fl & 2;
         int ylo, yn, xlo, xn;
@@ -57,25 +72,30 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
         float wysum = 0.f, wxsum = 0.f;
         for (int j = 0; j < yn; ++j) wysum += aa_weight(j, ylo, yc, yinv);
         for (int j = 0; j < xn; ++j) wxsum += aa_weight(j, xlo, xc, xinv);
+        // normalised column weights, evaluated once per output pixel (ATen divides every weight by the window's sum)
+        float wxs[PP_MAXW];
+#pragma unroll
+        for (int j = 0; j < PP_MAXW; ++j) wxs[j] = (j < xn) ? aa_weight(j, xlo, xc, xinv) / wxsum : 0.f;
+        auto wx_of = [&](int j) { return (xn <= PP_MAXW) ? wxs[j] : aa_weight(j, xlo, xc, xinv) / wxsum; };
         if (a.bgr) {
-            float con = -1.f, bri = 0.f;
-            if (a.jitter) { con = a.jitter[2 * b]; bri = a.jitter[2 * b + 1]; }
             float acc[3] = {0.f, 0.f, 0.f};
             for (int jy = 0; jy < yn; ++jy) {
                 const float wy = aa_weight(jy, ylo, yc, yinv) / wysum;
                 const int sy = fly ? a.H - 1 - (ylo + jy) : ylo + jy;             // the flip precedes the resize
                 const uint8_t* row = a.bgr + ((long long)b * a.H + sy) * a.W * 3;
                 float racc[3] = {0.f, 0.f, 0.f};
-                for (int jx = 0; jx < xn; ++jx) {
-                    const float wx = aa_weight(jx, xlo, xc, xinv) / wxsum;
+                auto tap = [&](int jx, float wx) {
                     const int sx = flx ? a.W - 1 - (xlo + jx) : xlo + jx;
                     const uint8_t* px = row + sx * 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float v = (float)px[2 - c] / 255.f;                      // BGR -> RGB, / 255.
-                        if (con >= 0.f) v = fminf(fmaxf(0.5f + con * (v - 0.5f) + bri, 0.f), 1.f);
-                        racc[c] = fmaf(wx, v, racc[c]);
-                    }
+                    for (int c = 0; c < 3; ++c) racc[c] = fmaf(wx, lut[px[2 - c]], racc[c]);   // BGR -> RGB, /255, jitter
+                };
+                if (xn <= PP_MAXW) {
+#pragma unroll
+                    for (int jx = 0; jx < PP_MAXW; ++jx)
+                        if (jx < xn) tap(jx, wxs[jx]);
+                } else {
+                    for (int jx = 0; jx < xn; ++jx) tap(jx, wx_of(jx));
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, racc[c], acc[c]);
@@ -95,7 +115,7 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
                 for (int jy = 0; jy < yn; ++jy) {
                     const float wy = aa_weight(jy, ylo, yc, yinv) / wysum;
                     float r = 0.f;
-                    for (int jx = 0; jx < xn; ++jx) r = fmaf(aa_weight(jx, xlo, xc, xinv) / wxsum, at(ylo + jy, xlo + jx), r);
+                    for (int jx = 0; jx < xn; ++jx) r = fmaf(wx_of(jx), at(ylo + jy, xlo + jx), r);
                     v = fmaf(wy, r, v);
                 }
             } else {

@@ -356,6 +356,12 @@ def stage_rows2():
         fma = B * C * H * W * ks * ks
         print(f"psf_conv B{B} {H}x{W} k{ks} grid{grid}: {ms:.3f} ms  {B * C * H * W / ms / 1e3:.1f} Mpix*ch/s  {fma / ms / 1e9:.2f} TFMA/s "
               f"(fp32 FFMA peak 148 SM x 128 x 1.9 GHz = 36 TFMA/s)", flush=True)
+    bgr = torch.randint(0, 255, (8, 1024, 1280, 3), dtype=torch.uint8, device="cuda")
+    d16 = torch.randint(0, 8000, (8, 1024, 1280), dtype=torch.int16, device="cuda").view(torch.uint16)
+    ms = timeit(lambda: aadff_b200.preprocess_rgbd(bgr, d16, (480, 640)))
+    gb = (bgr.numel() + d16.numel() * 2 + 8 * 4 * 480 * 640 * 4) / 1e9
+    print(f"preprocess_rgbd 8 x 1024x1280 -> 480x640 (image + depth): {ms:.3f} ms  {8 / ms:.1f} images/ms  {gb / ms * 1e3:.0f} GB/s of "
+          f"algorithmic traffic (5 B per input pixel + 16 B per output pixel)", flush=True)
     # fitting step: bs = 128 as in the reference (psfnet.py:79)
     ks, bs = 11, 128
     lens = aadff_b200.PSFNet(kernel_size=ks, device="cuda")
