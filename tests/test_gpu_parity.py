@@ -690,6 +690,20 @@ def test_c2_tensor_core_vs_fp32_full_size(lens):
     assert bool(((out >= mn.unsqueeze(2) - 1e-5) & (out <= mx.unsqueeze(2) + 1e-5)).all())   # convex combination
 
 
+def test_c3_linearity_in_the_image_at_full_size(lens):
+    """For fixed depth and focus the render is linear in the image (the PSFs do not depend on it): a size-independent
+    property checked on the whole c3 batch (16 x 5 x 256 x 256) -- render(a*x + b*y) == a*render(x) + b*render(y) up to
+    fp32 rounding of the 121-tap sums, and the constant offset passes through unchanged (sum of a PSF = 1)."""
+    img, dm = orc.synthetic_rgbd(16, 256, 256, seed=31)
+    img2, _ = orc.synthetic_rgbd(16, 256, 256, seed=32)
+    foc = -orc.synthetic_focus(dm, 5).cuda() * 1e3
+    dep = -dm.cuda() * 1e3
+    x, y = img.cuda(), img2.cuda()
+    rx, ry = lens.render_stack(x, dep, foc), lens.render_stack(y, dep, foc)
+    mix = lens.render_stack(0.25 * x + 0.5 * y + 0.125, dep, foc)
+    assert float((mix - (0.25 * rx + 0.5 * ry + 0.125)).abs().max()) < 2e-6
+
+
 def test_c3_batch_independence(lens):
     """c3 (16 x 5 x 256 x 256): rendering the batch == rendering each image alone, bit for bit."""
     img, dm = orc.synthetic_rgbd(16, 256, 256, seed=77)
