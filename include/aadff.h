@@ -34,6 +34,8 @@ extern "C" {
 #define AADFF_MODE_FAST 1   /* tcgen05, single fp16 term: max-abs <= 3e-2 on noise images, see DESIGN.md */
 #define AADFF_MODE_FP32 2   /* CUDA-core fp32 FFMA, operation-for-operation with the reference          */
 #define AADFF_MODE_MIXED 3  /* tcgen05, 3 terms for the first three MMA layers, 1 term afterwards        */
+/* (The first AADFF_MODE_ECON call on a handle runs the weight calibration on the host and uploads the result: that one
+ *  call allocates and synchronises -- make it outside CUDA-graph capture, e.g. as the usual warm-up call.)            */
 #define AADFF_MODE_ECON 4   /* tcgen05, 3 terms for L1-L4, 2 terms (Ah*Wh + Al*Wh) for L5.. and the head on fp16 weights
                                whose rounding is calibrated at create time to minimise the layer's output error over
                                the network's input box (csrc/econ_calib.h): 21 % fewer MMAs, max-abs 2e-5 .. 4e-5   */
