@@ -741,6 +741,38 @@ def test_multi_gpu_sharded_render_matches_single_gpu():
     assert res.returncode == 0 and "MULTI_GPU_VERIFY PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+def test_second_device_in_one_process(pkg):
+    """One process, two GPUs: everything on cuda:1 while cuda:0 stays the current device (the per-device shared-memory
+    opt-in of the large-kernel gather / thin lens was once cached per process -- ADVICE r01).  Skips on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from deeplens.psfnet import ThinLens
+    from deeplens.render_psf import local_psf_render
+    dev = torch.device("cuda:1")
+    assert torch.cuda.current_device() == 0
+    l1 = pkg.PSFNet(kernel_size=11, device="cuda:1")
+    l1.load_net(CKPT)
+    l0 = pkg.PSFNet(kernel_size=11, device="cuda:0")
+    l0.load_net(CKPT)
+    img, dm = orc.synthetic_rgbd(1, 40, 56, seed=5)
+    foc = -orc.synthetic_focus(dm, 3) * 1e3
+    for mode in ("parity", "econ", "fp32"):
+        a = l0.render_stack(img.cuda(0), -dm.cuda(0) * 1e3, foc.cuda(0), mode=mode)
+        b = l1.render_stack(img.to(dev), -dm.to(dev) * 1e3, foc.to(dev), mode=mode)
+        assert b.device == dev and torch.equal(a.cpu(), b.cpu()), mode
+    gen = torch.Generator().manual_seed(1)
+    im = torch.rand(1, 3, 20, 24, generator=gen)
+    psf = torch.rand(1, 20, 24, 31, 31, generator=gen)                  # ks = 31, 3 channels: > 48 KB of shared memory
+    for d in (dev, torch.device("cuda:0")):
+        assert maxabs(local_psf_render(im.to(d), psf.to(d), 31), orc.local_psf_render(im, psf, 31)) < 5e-4
+    tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=31, sensor_size=[36.0, 24.0], sensor_res=(96, 160)).to(dev)
+    im = torch.rand(1, 3, 96, 160, generator=gen)
+    dp = 300 + 6000 * torch.rand(1, 1, 96, 160, generator=gen)
+    fc = torch.tensor([1500.0])
+    assert maxabs(tl.render(im.to(dev), dp.to(dev), fc.to(dev)), orc.thinlens_render(im, dp, fc, 31, 50.0, 1.8, tl.ps)) < 5e-6
+    assert torch.cuda.current_device() == 0
+
+
 def test_simulate_focal_stack_matches_training_loop(lens):
     """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
     from dff.utils import select_focus_dist
