@@ -773,6 +773,52 @@ def test_second_device_in_one_process(pkg):
     assert torch.cuda.current_device() == 0
 
 
+def test_install_grafts_cuda_path_onto_the_unmodified_reference():
+    """aadff_b200.install() on the REAL reference (the unmodified copy in baseline/_ref, imported first): the reference's
+    own PSFNet -- ray-traced Lensgroup constructor, its own MLP module -- renders through libaadff.so afterwards and
+    reproduces the reference golden; uninstall() gives the eager path back.  Runs in a child process (the reference's
+    `deeplens` and the shadow package cannot share an interpreter); skips where baseline/_ref is absent."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile(os.path.join(root, "baseline", "_ref", "deeplens", "psfnet.py")):
+        pytest.skip("baseline/_ref (copy of the reference) not present")
+    code = f"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from baseline import ref_import
+ref_psfnet = ref_import.import_reference()
+sd = torch.load({CKPT!r}, map_location='cpu')
+lens = ref_import.make_lens(11, (480, 640), 'cuda', sd)
+assert type(lens).__module__ == 'deeplens.psfnet' and 'baseline/_ref' in sys.modules['deeplens.psfnet'].__file__
+g = np.load({os.path.join(GOLDEN, 'kat_b_2x64x64.npz')!r})
+n, c, h, w = np.meshgrid(np.arange(2), np.arange(3), np.arange(64), np.arange(64), indexing='ij')
+img = torch.tensor(((7 * h + 13 * w + 29 * c + 101 * n) % 256) / 255.0, dtype=torch.float32).cuda()
+n, h, w = np.meshgrid(np.arange(2), np.arange(64), np.arange(64), indexing='ij')
+dm = torch.tensor(0.5 + 4.5 * (((h * 64 + w) * 31 + 17 * n) % 1000) / 999.0, dtype=torch.float32).unsqueeze(1).cuda()
+foc = torch.tensor(g['foc']).cuda()
+eager = lens.render(img, -dm * 1e3, foc)                     # the reference's own eager path
+import aadff_b200
+launches0 = aadff_b200.native.lib.aadff_launch_count()
+assert aadff_b200.install() is True
+ours = lens.render(img, -dm * 1e3, foc)                      # same object, same call: now the fused kernel
+assert aadff_b200.native.lib.aadff_launch_count() == launches0 + 1
+gold = torch.tensor(g['out'])
+assert float((ours.cpu() - gold).abs().max()) < 2e-5 and float((eager.cpu() - gold).abs().max()) < 2e-5
+stack = lens.render_stack(img, -dm * 1e3, torch.stack([foc, foc * 1.5], 1))
+assert stack.shape == (2, 3, 2, 64, 64) and torch.equal(stack[:, :, 0], ours)
+psf = lens.pred(torch.tensor([[0., 0., .5, .5]]).cuda())
+assert abs(float(psf[0, 5, 5]) - 0.810939252) < 1e-6         # SURVEY.md 8c literal, through the grafted pred
+aadff_b200.uninstall()
+back = lens.render(img, -dm * 1e3, foc)
+assert aadff_b200.native.lib.aadff_launch_count() == launches0 + 3 and torch.equal(back, eager)
+print('INSTALL-GPU-OK')
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PYTHONPATH=""))
+    assert res.returncode == 0 and "INSTALL-GPU-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+
+
 def test_simulate_focal_stack_matches_training_loop(lens):
     """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
     from dff.utils import select_focus_dist
