@@ -819,6 +819,71 @@ print('INSTALL-GPU-OK')
     assert res.returncode == 0 and "INSTALL-GPU-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
 
 
+def test_reference_training_script_runs_unchanged_on_the_shadow_package(tmp_path):
+    """The reference's own 2_aber_aware_dff_aif.py -- byte for byte the copy in baseline/_ref -- executed with the shadow
+    directory in front of the reference on PYTHONPATH: config(), get_lens, get_dataset (the reference's Matterport3D /
+    Middlebury classes on a tiny synthetic dataset), two training iterations (select_focus_dist + 8 x lens.render +
+    AiFDepthNet forward/backward) and one validate() pass.  Only data is adapted: the YAML (1 epoch, no pretrained DFF
+    checkpoint, which the reference does not ship) and the dataset directory.  Optional packages this image lacks
+    (wandb, skimage, matplotlib, lpips) are stubbed through sitecustomize.  Asserts that the fused kernel did the renders."""
+    import shutil
+    import subprocess
+    import sys
+    import cv2 as cv
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "2_aber_aware_dff_aif.py")):
+        pytest.skip("baseline/_ref (copy of the reference) not present")
+    work = tmp_path / "work"
+    for d in ("configs", "lenses/rf50mm", "ckpt/rf50mm", "stubs"):
+        (work / d).mkdir(parents=True)
+    shutil.copy(os.path.join(ref, "2_aber_aware_dff_aif.py"), work / "2_aber_aware_dff_aif.py")
+    shutil.copy(os.path.join(ref, "lenses/rf50mm/lens.json"), work / "lenses/rf50mm/lens.json")
+    shutil.copy(os.path.join(ref, "ckpt/rf50mm/PSFNet480x640_ks11.pkl"), work / "ckpt/rf50mm/PSFNet480x640_ks11.pkl")
+    yml = open(os.path.join(ref, "configs/aber_aware_dff_aif.yml")).read()
+    yml = yml.replace("dffnet_pretrained: './ckpt/rf50mm/aifnet_stack8_480x640.pkl'", "dffnet_pretrained: ''").replace("epochs: 20", "epochs: 1")
+    assert "dffnet_pretrained: ''" in yml and "epochs: 1 " in yml
+    (work / "configs/aber_aware_dff_aif.yml").write_text(yml)
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:480, 0:640]
+    for i in range(2):
+        img = np.stack([(127 + 90 * np.sin(xx / (9.0 + i) + c) * np.cos(yy / 7.0)).clip(0, 255) for c in range(3)], -1).astype(np.uint8)
+        dep = (6000 + 4000 * np.sin(xx / 50.0 + i) + 3000 * (yy > 200)).astype(np.uint16)          # / 4000 -> metres
+        a = work / f"dataset/Matterport3D/train/aif/scene0/undistorted_color_images"
+        b = work / f"dataset/Matterport3D/train/depth/scene0/render_depth"
+        a.mkdir(parents=True, exist_ok=True); b.mkdir(parents=True, exist_ok=True)
+        cv.imwrite(str(a / f"{i}.jpg"), img); cv.imwrite(str(b / f"{i}.png"), dep)
+    m = work / "dataset/Middlebury2014/sceneA"
+    m.mkdir(parents=True)
+    cv.imwrite(str(m / "im0.png"), img); cv.imwrite(str(m / "depth.png"), (dep // 4).astype(np.uint16))   # mm
+    (work / "stubs/sitecustomize.py").write_text("""
+import sys, types, atexit
+for name in ["matplotlib", "matplotlib.pyplot", "lpips", "skimage", "skimage.metrics", "skimage.morphology", "skimage.filters", "wandb"]:
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["skimage.metrics"].peak_signal_noise_ratio = lambda *a, **k: 0.0
+sys.modules["skimage.metrics"].structural_similarity = lambda *a, **k: 0.0
+sys.modules["skimage.morphology"].disk = sys.modules["skimage.morphology"].closing = lambda *a, **k: None
+import scipy.ndimage
+sys.modules.setdefault("scipy.ndimage.interpolation", scipy.ndimage)
+def _report():
+    nat = sys.modules.get("aadff_native")
+    lens = sys.modules.get("deeplens.psfnet")
+    print("AADFF-LAUNCHES", nat.lib.aadff_launch_count() if nat else -1, getattr(lens, "__file__", None), flush=True)
+atexit.register(_report)
+""")
+    shadow = os.path.join(root, "aberration-aware-depth-from-focus_b200")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(work / "stubs"), shadow, ref]))
+    res = subprocess.run([sys.executable, "2_aber_aware_dff_aif.py"], cwd=work, capture_output=True, text=True, timeout=900, env=env)
+    tail = res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.returncode == 0, tail
+    line = [l for l in res.stdout.splitlines() if l.startswith("AADFF-LAUNCHES")][-1].split()
+    # 2 training iterations x (1 select_focus + 8 renders) + 1 validation image x (1 + 8) launches of libaadff kernels
+    assert int(line[1]) >= 27 and "aberration-aware-depth-from-focus_b200" in line[2], line
+    results = [d for d in (work / "results").iterdir()]
+    assert results and (results[0] / "depth_net_last.pkl").exists(), tail
+
+
 def test_simulate_focal_stack_matches_training_loop(lens):
     """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
     from dff.utils import select_focus_dist
