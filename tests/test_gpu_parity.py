@@ -884,6 +884,35 @@ atexit.register(_report)
     assert results and (results[0] / "depth_net_last.pkl").exists(), tail
 
 
+def test_reference_warm_up_script_runs_unchanged_on_the_shadow_package(tmp_path):
+    """0_warm_up.py (BASELINE configs[0]) itself, byte for byte from baseline/_ref, on the shadow package: the script's
+    image files are synthetic (the reference checkout ships no Middlebury RGB), everything else is the script."""
+    import shutil
+    import subprocess
+    import sys
+    import cv2 as cv
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "0_warm_up.py")):
+        pytest.skip("baseline/_ref (copy of the reference) not present")
+    work = tmp_path / "work"
+    for d in ("lenses/rf50mm", "ckpt/rf50mm", "datasets/Middlebury2014/Adirondack-perfect"):
+        (work / d).mkdir(parents=True)
+    shutil.copy(os.path.join(ref, "0_warm_up.py"), work / "0_warm_up.py")
+    shutil.copy(os.path.join(ref, "lenses/rf50mm/lens.json"), work / "lenses/rf50mm/lens.json")
+    shutil.copy(os.path.join(ref, "ckpt/rf50mm/PSFNet480x640_ks11.pkl"), work / "ckpt/rf50mm/PSFNet480x640_ks11.pkl")
+    g = load_golden("kat_k_warmup_c1.npz")
+    cv.imwrite(str(work / "datasets/Middlebury2014/Adirondack-perfect/im0.png"), cv.cvtColor(g["img_u8"], cv.COLOR_RGB2BGR))
+    cv.imwrite(str(work / "datasets/Middlebury2014/Adirondack-perfect/depth.png"), (g["depth_m"] * 1000).round().astype(np.uint16))
+    shadow = os.path.join(root, "aberration-aware-depth-from-focus_b200")
+    res = subprocess.run([sys.executable, "0_warm_up.py"], cwd=work, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PYTHONPATH=os.pathsep.join([shadow, ref])))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    out = cv.cvtColor(cv.imread(str(work / "aberrated_defocused_img.png")), cv.COLOR_BGR2RGB).astype(np.float32) / 255
+    ref_sub = np.transpose(g["out_sub"][0], (1, 2, 0))                        # the reference's CPU render of the same inputs
+    assert out.shape == (480, 640, 3) and float(np.abs(out[::3, ::3] - ref_sub).max()) < 1.5 / 255     # 8-bit PNG rounding
+
+
 def test_simulate_focal_stack_matches_training_loop(lens):
     """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
     from dff.utils import select_focus_dist
