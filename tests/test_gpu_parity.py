@@ -913,6 +913,22 @@ def test_reference_warm_up_script_runs_unchanged_on_the_shadow_package(tmp_path)
     assert out.shape == (480, 640, 3) and float(np.abs(out[::3, ::3] - ref_sub).max()) < 1.5 / 255     # 8-bit PNG rounding
 
 
+def test_fitting_with_the_reference_ray_tracer_and_the_device_trainer():
+    """Row f3 as SURVEY 8f frames it: the ray-traced training targets stay in the reference's Python
+    (PSFNet.get_training_data on the unmodified copy in baseline/_ref), the optimisation of train_psfnet runs on the
+    device through the grafted method (tests/gpu_fit_with_reference_raytracer.py, child process)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile(os.path.join(root, "baseline", "_ref", "deeplens", "psfnet.py")):
+        pytest.skip("baseline/_ref (copy of the reference) not present")
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_fit_with_reference_raytracer.py"), "20"],
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, PYTHONPATH=""))
+    assert res.returncode == 0 and "FIT-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+    losses = [float(x.strip("'")) for x in res.stdout.split("losses: [")[1].split("]")[0].split(", ")]
+    assert len(losses) == 2 and all(0 < l < 1e-3 for l in losses), losses
+
+
 def test_simulate_focal_stack_matches_training_loop(lens):
     """The block 2_aber_aware_dff_aif.py:101-114 (select_focus_dist + S renders + stack) as one call."""
     from dff.utils import select_focus_dist
