@@ -465,16 +465,20 @@ def test_weight_update_rebuilds_device_copy(pkg):
 
 
 def test_host_buffer_entry_point(pkg, lens):
+    """aadff_render_stack_host_f32 (host buffers; upload / compute / download pipelined over two parts: image halves for
+    N >= 2, row bands for a single image) returns exactly what the device-pointer call returns."""
     nat = pkg.native
-    img, dm = orc.synthetic_rgbd(2, 40, 48, seed=3)
-    foc = -orc.synthetic_focus(dm, 4) * 1e3
-    dep = (-dm * 1e3).reshape(2, 40, 48).contiguous()
-    out = torch.empty(2, 3, 4, 40, 48)
-    nat.check(nat.lib.aadff_render_stack_host_f32(lens.native().handle, img.data_ptr(), dep.data_ptr(),
-                                                  foc.contiguous().data_ptr(), out.data_ptr(), 2, 3, 4, 40, 48,
-                                                  -200.0, -20000.0, nat.MODE_PARITY))
-    dev = lens.render_stack(img.cuda(), dep.cuda(), foc.cuda(), mode="parity")
-    assert torch.equal(out, dev.cpu())
+    for (N, S, H, W, mode) in [(2, 4, 40, 48, "parity"), (3, 2, 24, 40, "parity"), (1, 3, 64, 48, "parity"), (1, 2, 37, 50, "fp32"),
+                               (1, 1, 5, 9, "parity"), (1, 5, 128, 96, "econ")]:
+        img, dm = orc.synthetic_rgbd(N, H, W, seed=3 + H)
+        foc = -orc.synthetic_focus(dm, S) * 1e3
+        dep = (-dm * 1e3).reshape(N, H, W).contiguous()
+        out = torch.full((N, 3, S, H, W), -1.0)
+        nat.check(nat.lib.aadff_render_stack_host_f32(lens.native().handle, img.data_ptr(), dep.data_ptr(),
+                                                      foc.contiguous().data_ptr(), out.data_ptr(), N, 3, S, H, W,
+                                                      -200.0, -20000.0, nat.MODES[mode]))
+        dev = lens.render_stack(img.cuda(), dep.cuda(), foc.cuda(), mode=mode)
+        assert torch.equal(out, dev.cpu()), (N, S, H, W, mode)
 
 
 def test_c_abi_error_codes(pkg, lens):
