@@ -50,3 +50,20 @@ for _ in range(2):
 torch.cuda.synchronize()
 print("trainer loss", float(loss))
 tr.close()
+# ---- thin lens with TMA tensor-tile halo (interior tiles) and the cp.async border path, large kernel (single buffer), preparation
+tl2 = aadff_b200.ThinLens(50.0, 1.8, 11, [36.0, 24.0], (72, 200)).to("cuda")
+im2 = torch.rand(2, 3, 72, 200, device="cuda")
+dp2 = 300 + 6000 * torch.rand(2, 1, 72, 200, device="cuda")
+print("thinlens TMA", float(tl2.render(im2, dp2, torch.tensor([1500.0, 2500.0], device="cuda")).mean()))
+tl3 = aadff_b200.ThinLens(50.0, 1.8, 31, [36.0, 24.0], (96, 160)).to("cuda")
+print("thinlens k31", float(tl3.render(torch.rand(1, 4, 96, 160, device="cuda"), 300 + 6000 * torch.rand(1, 1, 96, 160, device="cuda"),
+                                       torch.tensor([1500.0], device="cuda")).mean()))
+bgr = torch.randint(0, 255, (2, 96, 130, 3), dtype=torch.uint8, device="cuda")
+d16 = torch.randint(0, 8000, (2, 96, 130), dtype=torch.int16, device="cuda").view(torch.uint16)
+a, d = aadff_b200.preprocess_rgbd(bgr, d16, (40, 56), jitter=torch.tensor([[0.5, 0.1], [-1.0, 0.0]]), flips=torch.tensor([3, 0], dtype=torch.uint8))
+print("preprocess", float(a.mean()), float(d.mean()))
+aadff_b200.native.lib.aadff_debug_set_flags(32)
+print("fast two tiles", float(lens.render_stack(img, dep, foc, mode="fast").mean()))
+aadff_b200.native.lib.aadff_debug_set_flags(8)
+print("cluster multicast", float(lens.render_stack(img, dep, foc, mode="parity").mean()))
+aadff_b200.native.lib.aadff_debug_set_flags(0)
