@@ -16,6 +16,7 @@
 #include "fused_fast2_kernel.cuh"
 #include "gather_kernel.cuh"
 #include "gather_coalesced_kernel.cuh"
+#include "gather_strip_kernel.cuh"
 #include "mlp_fp32_kernel.cuh"
 #include "thinlens_kernel.cuh"
 #include "focus_kernel.cuh"
@@ -67,6 +68,52 @@ bool launch_gather_coalesced(int ks, int cn, int grid, cudaStream_t st, const fl
     return launch_gc_ks<3>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
 }
 
+// Strip-walking gather (gather_strip_kernel.cuh), ks <= 15: slots per warp / warps per CTA chosen so that the PSF
+// slots and the per-warp halo rings fill the 227 KB of shared memory.  `alt` = the deeper-ring / fewer-warps
+// variant (debug flag 1024), kept for A/B timing.
+template <int KS> struct StripPlan;
+template <> struct StripPlan<3>  { static constexpr int SL = 4, NW = 16, SL2 = 2, NW2 = 16; };
+template <> struct StripPlan<5>  { static constexpr int SL = 2, NW = 12, SL2 = 3, NW2 = 9; };
+template <> struct StripPlan<7>  { static constexpr int SL = 1, NW = 11, SL2 = 2, NW2 = 7; };
+template <> struct StripPlan<9>  { static constexpr int SL = 1, NW = 7,  SL2 = 2, NW2 = 4; };
+template <> struct StripPlan<11> { static constexpr int SL = 1, NW = 5,  SL2 = 2, NW2 = 3; };
+template <> struct StripPlan<13> { static constexpr int SL = 2, NW = 2,  SL2 = 1, NW2 = 4; };
+template <> struct StripPlan<15> { static constexpr int SL = 1, NW = 3,  SL2 = 3, NW2 = 1; };
+// ks = 17 / 19 fit two warps only and measured 0.61 / 0.63 of the HBM peak against 0.72 / 0.78 for the
+// register-streaming kernel: the strip kernel stops at 15 (0.83 against 0.71).
+
+template <int KS, int CN, int SL, int NW>
+void launch_gs(int sms, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
+               int c0) {
+    constexpr int smem = StripCfg<KS, CN>::SMEM_BYTES(SL, NW);
+    static_assert(smem <= 232448, "strip gather: shared memory plan does not fit");
+    if (smem > 48 * 1024)      // per-device attribute: set on every launch that needs the opt-in
+        cudaFuncSetAttribute(local_psf_strip_kernel<KS, CN, SL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const long long rows = (long long)N * ((W + GSW_PX - 1) / GSW_PX) * H;
+    const int grid = (int)std::min<long long>((rows + NW - 1) / NW, sms);
+    local_psf_strip_kernel<KS, CN, SL, NW><<<grid, NW * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
+}
+template <int KS>
+bool launch_gs_ks(int ks, int cn, bool alt, int sms, cudaStream_t st, const float* img, const float* psf, float* out,
+                  int N, int C, int H, int W, int c0) {
+    if constexpr (KS > 15) {
+        return false;
+    } else {
+        if (ks == KS) {
+            using P = StripPlan<KS>;
+            if (cn == 3) {
+                if (alt) launch_gs<KS, 3, P::SL2, P::NW2>(sms, st, img, psf, out, N, C, H, W, c0);
+                else launch_gs<KS, 3, P::SL, P::NW>(sms, st, img, psf, out, N, C, H, W, c0);
+            } else {
+                if (alt) launch_gs<KS, 1, P::SL2, P::NW2>(sms, st, img, psf, out, N, C, H, W, c0);
+                else launch_gs<KS, 1, P::SL, P::NW>(sms, st, img, psf, out, N, C, H, W, c0);
+            }
+            return true;
+        }
+        return launch_gs_ks<KS + 2>(ks, cn, alt, sms, st, img, psf, out, N, C, H, W, c0);
+    }
+}
+
 template <int KS>
 bool launch_psf_conv(int ks, int grid, cudaStream_t st, const PsfConvArgs& a) {
     if constexpr (KS > 31) {
@@ -92,6 +139,35 @@ bool launch_thinlens(int ks, int grid, int smem, cudaStream_t st, const ThinLens
             return true;
         }
         return launch_thinlens<KS + 2>(ks, grid, smem, st, a, map);
+    }
+}
+// two pixels per thread (thinlens_render2_kernel): tile geometry by kernel size
+template <int KS>
+bool thinlens2_geometry(int ks, int cn, int* box_w, int* box_h, int* smem) {
+    if constexpr (KS > 31) {
+        return false;
+    } else {
+        if (ks == KS) {
+            *box_w = ThinLens2Cfg<KS>::BW;
+            *box_h = ThinLens2Cfg<KS>::HH;
+            *smem = ThinLens2Cfg<KS>::SMEM_BYTES(cn);
+            return true;
+        }
+        return thinlens2_geometry<KS + 2>(ks, cn, box_w, box_h, smem);
+    }
+}
+template <int KS>
+bool launch_thinlens2(int ks, int grid, int smem, cudaStream_t st, const ThinLensArgs& a, const CUtensorMap& map) {
+    if constexpr (KS > 31) {
+        return false;
+    } else {
+        if (ks == KS) {
+            if (smem > 48 * 1024)      // per-device attribute
+                cudaFuncSetAttribute(thinlens_render2_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            thinlens_render2_kernel<KS><<<grid, TL_NT, smem, st>>>(a, map);
+            return true;
+        }
+        return launch_thinlens2<KS + 2>(ks, grid, smem, st, a, map);
     }
 }
 
@@ -844,6 +920,21 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int dbg = g_dbg_flags.load();
+    if (ks >= 3 && ks <= 15 && !(dbg & (128 | 512)) && W % 4 == 0 && reinterpret_cast<uintptr_t>(psf) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 8 == 0 && (long long)N * H * ((W + GSW_PX - 1) / GSW_PX) < (1ll << 40)) {
+        // strip-walking kernel (gather_strip_kernel.cuh): bulk-copied PSF rows, per-warp pipelines
+        int c0 = 0;
+        while (c0 < C) {
+            const int cn = (C - c0 >= 3) ? 3 : 1;
+            if (!launch_gs_ks<3>(ks, cn, (dbg & 1024) != 0, sms, st, img, psf, out, N, C, H, W, c0))
+                return fail(AADFF_E_INVALID, "unsupported kernel size");
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+            c0 += cn;
+        }
+        return AADFF_OK;
+    }
     if (ks >= 3 && ks <= 31 && !(g_dbg_flags.load() & 128)) {
         // register-streaming kernel (gather_coalesced_kernel.cuh): any W, any alignment
         const long long tiles = (long long)N * ((H + GC_WARPS - 1) / GC_WARPS) * ((W + GC_TW - 1) / GC_TW);
@@ -941,21 +1032,25 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
     a.foc_len = foc_len; a.ps = pixel_size; a.d_lo = d_lo; a.d_hi = d_hi; a.flip = flip_sign ? 1 : 0;
     a.flip_dev = flip_sign_dev;
     if (ks > 31) return fail(AADFF_E_UNSUPPORTED, "thin-lens kernel sizes above 31 are not built");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool two_px = !(g_dbg_flags.load() & 2048);        // 2048: the one-pixel-per-thread kernel (A/B timing)
     const int tl_r = (ks - 1) / 2, tl_sh = (4 - tl_r % 4) % 4;
-    const int HH = TL_TILE_H + ks - 1, BW = (TL_TILE_W + ks - 1 + tl_sh + 3) / 4 * 4;      // = ThinLensCfg<ks>::BW
-    const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + TL_TILE_W - 1) / TL_TILE_W);
+    const int tile_w = two_px ? TL2_TILE_W : TL_TILE_W;
+    const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + tile_w - 1) / tile_w);
     const int grid = (int)std::min<long long>(tiles, (long long)sms * 4);
     for (int c0 = 0; c0 < C; c0 += TL_MAXC) {
         a.c0 = c0;
         a.cn = std::min(TL_MAXC, C - c0);
-        const int smem = (ks <= 15 ? 2 : 1) * ((a.cn * HH * BW + 31) / 32 * 32) * 4 + 128;      // = ThinLensCfg<ks>::SMEM_BYTES(cn)
+        int HH = TL_TILE_H + ks - 1, BW = (TL_TILE_W + ks - 1 + tl_sh + 3) / 4 * 4;      // = ThinLensCfg<ks>::HH, BW
+        int smem = (ks <= 15 ? 2 : 1) * ((a.cn * HH * BW + 31) / 32 * 32) * 4 + 128;      // = ThinLensCfg<ks>::SMEM_BYTES(cn)
+        if (two_px && !thinlens2_geometry<1>(ks, a.cn, &BW, &HH, &smem)) return fail(AADFF_E_INVALID, "unsupported kernel size");
         if (smem > optin) return fail(AADFF_E_UNSUPPORTED, "kernel size too large for the shared-memory halo tile");
         // the image halo of interior tiles arrives as one TMA box [cn][HH][BW] of the [N*C, H, W] tensor
         CUtensorMap map;
         std::memset(&map, 0, sizeof(map));
         a.use_tma = make_image_map(&map, img, (long long)N * C, H, W, BW, HH, a.cn) && !(g_dbg_flags.load() & 16);
-        if (!launch_thinlens<1>(ks, grid, smem, static_cast<cudaStream_t>(stream), a, map))
-            return fail(AADFF_E_INVALID, "unsupported kernel size");
+        const bool launched = two_px ? launch_thinlens2<1>(ks, grid, smem, st, a, map) : launch_thinlens<1>(ks, grid, smem, st, a, map);
+        if (!launched) return fail(AADFF_E_INVALID, "unsupported kernel size");
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }

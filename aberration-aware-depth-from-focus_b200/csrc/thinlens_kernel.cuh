@@ -205,4 +205,193 @@ thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two pixels per thread (round 2, second version).  The one-pixel kernel above is issue-bound: per tap and pixel it
+// spends 3 LDS + 3 FFMA + FMUL + ISETP/FSEL + FADD.  Here a thread owns two horizontally adjacent pixels:
+//   * the weights of a PSF row depend on |dy| and |dx| only: for each |dy| the (k+1)/2 weights per pixel are formed
+//     once (FMUL + compare/select) and serve the rows -dy and +dy and both signs of dx; the normalising sum is taken
+//     from the same (k+1)/2 values -- nothing but LDS and FFMA is left per tap;
+//   * per PSF row and channel the thread loads ONE (k+1 [+1 for alignment])-wide window with LDS.64 and both pixels
+//     take their k taps from it: (k+3)/2 LDS.64 per 2k FFMA instead of 2k LDS.32.
+// CTA tile = 8 rows x 64 columns (warp = row, lane j = columns 2j, 2j+1); halo staging (TMA box / clamped cp.async,
+// double-buffered) as above.  ~5 instead of ~9 instructions per tap and pixel.
+constexpr int TL2_TILE_W = 64;
+
+template <int KS>
+struct ThinLens2Cfg {
+    static constexpr int R = (KS - 1) / 2;
+    static constexpr int HH = TL_TILE_H + KS - 1;
+    static constexpr int HW = TL2_TILE_W + KS - 1;
+    static constexpr int SH = (4 - R % 4) % 4;                  // box starts at a 16-byte aligned column (see above)
+    static constexpr int WOFF = SH & 1;                         // LDS.64 windows start at an even float index
+    static constexpr int NLD = (WOFF + KS + 1 + 1) / 2;         // float2 loads per window
+    static constexpr int BW = (HW + SH + 1 + 3) / 4 * 4;        // one spare column: the last window may read one float past the halo
+    static constexpr int CSTRIDE = HH * BW;
+    __host__ __device__ static constexpr int BUF_FLOATS(int cn) { return (cn * CSTRIDE + 31) / 32 * 32; }
+    static constexpr int NBUF = KS <= 15 ? 2 : 1;
+    __host__ __device__ static constexpr int SMEM_BYTES(int cn) { return NBUF * BUF_FLOATS(cn) * 4 + 128; }
+};
+
+template <int KS>
+__global__ void __launch_bounds__(TL_NT)
+thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap img_map) {
+    using Cfg = ThinLens2Cfg<KS>;
+    constexpr int R = Cfg::R, HH = Cfg::HH, HW = Cfg::HW, BW = Cfg::BW, SH = Cfg::SH, CSTRIDE = Cfg::CSTRIDE;
+    constexpr int WOFF = Cfg::WOFF, NLD = Cfg::NLD;
+    extern __shared__ __align__(128) unsigned char tl_smem[];
+    float* bufs = reinterpret_cast<float*>(tl_smem + 128);
+    const uint32_t bar0 = smem_u32(tl_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (a.W + TL2_TILE_W - 1) / TL2_TILE_W, tiles_y = (a.H + TL_TILE_H - 1) / TL_TILE_H;
+    const long long n_tiles = (long long)a.N * tiles_x * tiles_y;
+    const bool flip = a.flip_dev ? (*a.flip_dev != 0) : (a.flip != 0);
+    const int buf_floats = Cfg::BUF_FLOATS(a.cn);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto coords = [&](long long tile, int& n, int& h0, int& w0) {
+        const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+        n = (int)(tile / ((long long)tiles_x * tiles_y));
+        h0 = ty * TL_TILE_H;
+        w0 = tx * TL2_TILE_W;
+    };
+    auto interior = [&](int h0, int w0) {      // the halo lies inside the image (the box's alignment / spare columns may not: unused)
+        return a.use_tma && h0 - R >= 0 && w0 - R >= 0 && h0 - R + HH <= a.H && w0 - R + HW <= a.W;
+    };
+    auto issue_halo = [&](long long tile, int b) {
+        int n, h0, w0;
+        coords(tile, n, h0, w0);
+        float* dst = bufs + b * buf_floats;
+        if (interior(h0, w0)) {
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(bar0 + 8 * b, (uint32_t)(a.cn * CSTRIDE * 4));
+                tma_load_3d(smem_u32(dst), &img_map, w0 - R - SH, h0 - R, n * a.C + a.c0, bar0 + 8 * b);
+            }
+        } else {
+            const uint32_t d0 = smem_u32(dst);
+            for (int idx = threadIdx.x; idx < a.cn * HH * HW; idx += TL_NT) {
+                const int c = idx / (HH * HW), rem = idx - c * (HH * HW);
+                const int yy = rem / HW, xx = rem - yy * HW;
+                const int gy = min(max(h0 + yy - R, 0), a.H - 1), gx = min(max(w0 + xx - R, 0), a.W - 1);   // replicate
+                cp_async4(d0 + 4u * (uint32_t)(c * CSTRIDE + yy * BW + xx + SH),
+                          a.img + ((long long)(n * a.C + a.c0 + c) * a.H + gy) * a.W + gx);
+            }
+        }
+    };
+
+    constexpr bool DB = Cfg::NBUF == 2;
+    uint32_t phase = 0;
+    int cur = 0;
+    if (DB && (long long)blockIdx.x < n_tiles) issue_halo(blockIdx.x, 0);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int n, h0, w0;
+        coords(tile, n, h0, w0);
+        const int h = h0 + warp, w = w0 + 2 * lane;
+        // circle of confusion (ThinLens.coc, psfnet.py:503-511), operation order of the reference
+        float cexp[2] = {0.f, 0.f};
+        int r2c[2] = {0, 0};
+        bool ok[2];
+        const float f0 = __ldg(a.foc + n);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            ok[p] = (h < a.H) && (w + p < a.W);
+            if (ok[p]) {
+                float d = __ldg(a.depth + ((long long)n * a.H + h) * a.W + w + p);
+                float f = f0;
+                if (flip) { d = -d; f = -f; }
+                d = fminf(fmaxf(d, a.d_lo), a.d_hi);
+                float coc = a.k1 * fabsf(d - f);
+                coc = __fdiv_rn(coc, d);
+                coc = coc * a.foc_len;
+                coc = __fdiv_rn(coc, f - a.foc_len);
+                const float coc_px = fmaxf(__fdiv_rn(coc, a.ps), 0.1f);
+                const float rad = coc_px * 0.5f;
+                const float r2 = rad * rad;
+                cexp[p] = __fdiv_rn(-0.5f * 1.4426950408889634f, r2);    // exp(-d2/2/r2) = 2^(d2 * cexp)
+                r2c[p] = (r2 >= 4096.f) ? 4096 : (int)ceilf(r2);          // d2 < r2 as an integer compare (d2 <= 450)
+            }
+        }
+        if (!DB) issue_halo(tile, 0);
+        if (interior(h0, w0)) {
+            mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1);
+            phase ^= 1u << cur;
+        } else {
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        if (DB && tile + gridDim.x < n_tiles) issue_halo(tile + gridDim.x, cur ^ 1);
+
+        if (ok[0]) {
+            float g[2][R + 1];                                  // g[p][d] = 2^(d^2 cexp): the separable Gaussian factor
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int d = 0; d <= R; ++d) g[p][d] = exp2f((float)(d * d) * cexp[p]);
+            float acc[2][TL_MAXC], wsum[2] = {0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int c = 0; c < TL_MAXC; ++c) acc[p][c] = 0.f;
+            const float* ib = bufs + cur * buf_floats + warp * BW + (SH - WOFF) + 2 * lane;
+            // absent channels re-read channel 0 (results discarded at the store): no branches in the tap loop
+            const int cs[TL_MAXC] = {0, a.cn > 1 ? CSTRIDE : 0, a.cn > 2 ? 2 * CSTRIDE : 0};
+#pragma unroll 1
+            for (int da = 0; da <= R; ++da) {
+                float wt[2][R + 1];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const float gi = exp2f((float)(da * da) * cexp[p]);
+                    const int lim = r2c[p] - da * da;           // tap (dy, dx) is inside the disk iff dx^2 < lim
+                    float rs = 0.f;
+#pragma unroll
+                    for (int d = R; d >= 1; --d) {
+                        wt[p][d] = (d * d < lim) ? gi * g[p][d] : 0.f;      // psf_mask = (x^2 + y^2 < radius^2)
+                        rs += wt[p][d];
+                    }
+                    wt[p][0] = (0 < lim) ? gi : 0.f;            // g[p][0] = 1
+                    rs = fmaf(2.f, rs, wt[p][0]);
+                    wsum[p] += (da == 0) ? rs : 2.f * rs;
+                }
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    if (side == 1 && da == 0) break;
+                    const int i = side ? R + da : R - da;
+                    const float* prow = ib + i * BW;
+#pragma unroll
+                    for (int c = 0; c < TL_MAXC; ++c) {
+                        const float2* pw = reinterpret_cast<const float2*>(prow + cs[c]);
+                        float win[2 * NLD];
+#pragma unroll
+                        for (int l = 0; l < NLD; ++l) {
+                            const float2 v = pw[l];
+                            win[2 * l] = v.x;
+                            win[2 * l + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int p = 0; p < 2; ++p)
+#pragma unroll
+                            for (int j = 0; j < KS; ++j)
+                                acc[p][c] = fmaf(win[WOFF + p + j], wt[p][j <= R ? R - j : j - R], acc[p][c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                if (!ok[p]) continue;
+                const float inv = __fdiv_rn(1.0f, wsum[p]);     // the centre tap always passes the mask: wsum >= 1
+#pragma unroll
+                for (int c = 0; c < TL_MAXC; ++c)
+                    if (c < a.cn) a.out[((long long)(n * a.C + a.c0 + c) * a.H + h) * a.W + w + p] = acc[p][c] * inv;
+            }
+        }
+        __syncthreads();
+        if (DB) cur ^= 1;
+    }
+}
+
 }  // namespace aadff

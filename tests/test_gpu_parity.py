@@ -117,6 +117,40 @@ def test_gather_every_kernel_size_vs_oracle(pkg, ks):
         assert maxabs(old, ref) < 2e-6, (ks, N, C, H, W)
 
 
+@pytest.mark.parametrize("ks", [3, 5, 7, 9, 11, 13, 15, 17, 19])
+def test_gather_strip_kernel_vs_oracle_and_register_streaming(pkg, ks):
+    """Strip-walking gather (gather_strip_kernel.cuh; taken when W % 4 == 0 and ks <= 15; larger ks exercise the fall-through): partial strips (W = 68, 132,
+    200), a strip narrower than one lane pair (W = 4), images shorter than the kernel (H = 3), several images / strips
+    per warp run, C = 1 / 3 / 4, both shared-memory plans (debug flag 1024 = deeper ring), against the oracle's direct
+    definition and against the register-streaming kernel (debug flag 512)."""
+    from deeplens.render_psf import local_psf_render
+    gen = torch.Generator().manual_seed(300 + ks)
+    for (N, C, H, W) in [(2, 3, 19, 68), (1, 4, 33, 132), (1, 1, 3, 4), (1, 3, 70, 64), (3, 3, 9, 200)]:
+        img = torch.rand(N, C, H, W, generator=gen)
+        psf = torch.rand(N, H, W, ks, ks, generator=gen)
+        psf = psf / psf.sum((-1, -2), keepdim=True)
+        ref = orc.local_psf_render(img, psf, ks)
+        for flags in (0, 1024, 512):
+            pkg.native.lib.aadff_debug_set_flags(flags)
+            try:
+                out = local_psf_render(img.cuda(), psf.cuda(), ks)
+            finally:
+                pkg.native.lib.aadff_debug_set_flags(0)
+            assert out.shape == ref.shape
+            assert maxabs(out, ref) < 2e-6, (ks, flags, N, C, H, W)
+    # a launch that gives every warp of every SM a run crossing strip and image boundaries
+    img = torch.rand(5, 3, 96, 320, generator=gen).cuda()
+    psf = torch.rand(5, 96, 320, ks, ks, generator=gen).cuda()
+    psf = psf / psf.sum((-1, -2), keepdim=True)
+    new = local_psf_render(img, psf, ks)
+    pkg.native.lib.aadff_debug_set_flags(512)
+    try:
+        old = local_psf_render(img, psf, ks)
+    finally:
+        pkg.native.lib.aadff_debug_set_flags(0)
+    assert maxabs(new, old) < 2e-6, ks
+
+
 @pytest.mark.parametrize("hidden_layers", [0, 2, 5])
 def test_other_network_depths_vs_oracle(pkg, hidden_layers):
     """The C ABI takes any number of 256-wide hidden layers: shallower / deeper MLPs than the reference's
@@ -298,6 +332,31 @@ def test_thinlens_and_focus_golden(pkg):
     big = torch.rand(3, 1, 1080, 1920, generator=torch.Generator().manual_seed(1)) * 5
     big[big < 0.02] = 0.0
     assert torch.equal(select_focus_dist(big.cuda(), 7).cpu(), orc.select_focus_dist(big, 7))
+
+
+@pytest.mark.parametrize("ks", [3, 7, 11, 15, 17, 31])
+def test_thinlens_two_pixel_kernel_vs_oracle_and_one_pixel_kernel(pkg, ks):
+    """ThinLens.render's default kernel gives every thread two adjacent pixels (thinlens_render2_kernel: per-|dy| weight
+    rows, LDS.64 windows); debug flag 2048 selects the one-pixel-per-thread kernel.  Odd widths (the second pixel of the last
+    thread does not exist), W % 4 != 0 (no TMA), border-only and interior tiles, C = 1 / 3 / 5, against the oracle and
+    against the one-pixel kernel."""
+    from deeplens.psfnet import ThinLens
+    gen = torch.Generator().manual_seed(700 + ks)
+    for (N, C, H, W) in [(1, 1, 9, 13), (2, 3, 72, 200), (1, 5, 33, 67), (1, 3, 40, 264), (1, 2, 5, 64)]:
+        tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=ks, sensor_size=[36.0, 24.0], sensor_res=(H, W)).to("cuda")
+        im = torch.rand(N, C, H, W, generator=gen)
+        dp = 300 + 6000 * torch.rand(N, 1, H, W, generator=gen)
+        fc = 500 + 3000 * torch.rand(N, generator=gen)
+        got = tl.render(im.cuda(), dp.cuda(), fc.cuda())
+        pkg.native.lib.aadff_debug_set_flags(2048)
+        try:
+            one = tl.render(im.cuda(), dp.cuda(), fc.cuda())
+        finally:
+            pkg.native.lib.aadff_debug_set_flags(0)
+        assert maxabs(got, one) < 2e-6, (ks, N, C, H, W)
+        if ks <= 17:
+            ref = orc.thinlens_render(im, dp, fc, ks, 50.0, 1.8, tl.ps)
+            assert maxabs(got, ref) < 5e-6, (ks, N, C, H, W)
 
 
 def test_render_psf_and_psf_map_golden(pkg):
