@@ -68,49 +68,62 @@ bool launch_gather_coalesced(int ks, int cn, int grid, cudaStream_t st, const fl
     return launch_gc_ks<3>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
 }
 
-// Strip-walking gather (gather_strip_kernel.cuh), ks <= 15: slots per warp / warps per CTA chosen so that the PSF
-// slots and the per-warp halo rings fill the 227 KB of shared memory.  `alt` = the deeper-ring / fewer-warps
-// variant (debug flag 1024), kept for A/B timing.
+// Strip-walking gather (gather_strip_kernel.cuh), ks <= 15: slots per warp (SL) / warps per CTA (NW) / 64-column
+// passes per strip row (U) chosen so that the PSF slots and the per-warp halo rings fill the 227 KB of shared memory.
+// Plans are ordered widest strip first: the memory system likes long contiguous requests (ks = 7: 12.5 KB chunks reach
+// 0.79 of the HBM peak, 25 KB 0.84, 50 KB 0.88), but a strip width that does not divide W wastes the narrower last
+// strip (a chunk costs its latency, whatever its width): the first plan whose strips cover W with <= 10 % of padding
+// runs.  Debug flags 1024 / 4096 force plan 1 / 2 (A/B timing).
+struct StripShape { int SL, NW, U; };
 template <int KS> struct StripPlan;
-template <> struct StripPlan<3>  { static constexpr int SL = 4, NW = 16, SL2 = 2, NW2 = 16; };
-template <> struct StripPlan<5>  { static constexpr int SL = 2, NW = 12, SL2 = 3, NW2 = 9; };
-template <> struct StripPlan<7>  { static constexpr int SL = 1, NW = 11, SL2 = 2, NW2 = 7; };
-template <> struct StripPlan<9>  { static constexpr int SL = 1, NW = 7,  SL2 = 2, NW2 = 4; };
-template <> struct StripPlan<11> { static constexpr int SL = 1, NW = 5,  SL2 = 2, NW2 = 3; };
-template <> struct StripPlan<13> { static constexpr int SL = 2, NW = 2,  SL2 = 1, NW2 = 4; };
-template <> struct StripPlan<15> { static constexpr int SL = 1, NW = 3,  SL2 = 3, NW2 = 1; };
+template <> struct StripPlan<3>  { static constexpr StripShape P[3] = {{2, 7, 4}, {2, 12, 2}, {4, 16, 1}}; };
+template <> struct StripPlan<5>  { static constexpr StripShape P[3] = {{1, 5, 4}, {2, 6, 2}, {2, 12, 1}}; };
+template <> struct StripPlan<7>  { static constexpr StripShape P[3] = {{1, 3, 4}, {1, 6, 2}, {1, 11, 1}}; };
+template <> struct StripPlan<9>  { static constexpr StripShape P[3] = {{1, 3, 2}, {1, 7, 1}, {2, 4, 1}}; };
+template <> struct StripPlan<11> { static constexpr StripShape P[3] = {{1, 5, 1}, {2, 3, 1}, {2, 3, 1}}; };
+template <> struct StripPlan<13> { static constexpr StripShape P[3] = {{2, 2, 1}, {1, 4, 1}, {1, 4, 1}}; };
+template <> struct StripPlan<15> { static constexpr StripShape P[3] = {{1, 3, 1}, {3, 1, 1}, {3, 1, 1}}; };
 // ks = 17 / 19 fit two warps only and measured 0.61 / 0.63 of the HBM peak against 0.72 / 0.78 for the
 // register-streaming kernel: the strip kernel stops at 15 (0.83 against 0.71).
 
-template <int KS, int CN, int SL, int NW>
+template <int KS, int CN, int SL, int NW, int U>
 void launch_gs(int sms, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
                int c0) {
-    constexpr int smem = StripCfg<KS, CN>::SMEM_BYTES(SL, NW);
+    constexpr int smem = StripCfg<KS, CN, U>::SMEM_BYTES(SL, NW);
     static_assert(smem <= 232448, "strip gather: shared memory plan does not fit");
     if (smem > 48 * 1024)      // per-device attribute: set on every launch that needs the opt-in
-        cudaFuncSetAttribute(local_psf_strip_kernel<KS, CN, SL, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const long long rows = (long long)N * ((W + GSW_PX - 1) / GSW_PX) * H;
+        cudaFuncSetAttribute(local_psf_strip_kernel<KS, CN, SL, NW, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const long long rows = (long long)N * ((W + GSW_PX * U - 1) / (GSW_PX * U)) * H;
     const int grid = (int)std::min<long long>((rows + NW - 1) / NW, sms);
-    local_psf_strip_kernel<KS, CN, SL, NW><<<grid, NW * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
+    local_psf_strip_kernel<KS, CN, SL, NW, U><<<grid, NW * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
+}
+template <int KS, int I>
+void launch_gs_plan(int cn, int sms, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H,
+                    int W, int c0) {
+    constexpr StripShape S = StripPlan<KS>::P[I];
+    if (cn == 3) launch_gs<KS, 3, S.SL, S.NW, S.U>(sms, st, img, psf, out, N, C, H, W, c0);
+    else launch_gs<KS, 1, S.SL, S.NW, S.U>(sms, st, img, psf, out, N, C, H, W, c0);
 }
 template <int KS>
-bool launch_gs_ks(int ks, int cn, bool alt, int sms, cudaStream_t st, const float* img, const float* psf, float* out,
+bool launch_gs_ks(int ks, int cn, int plan, int sms, cudaStream_t st, const float* img, const float* psf, float* out,
                   int N, int C, int H, int W, int c0) {
     if constexpr (KS > 15) {
         return false;
     } else {
         if (ks == KS) {
-            using P = StripPlan<KS>;
-            if (cn == 3) {
-                if (alt) launch_gs<KS, 3, P::SL2, P::NW2>(sms, st, img, psf, out, N, C, H, W, c0);
-                else launch_gs<KS, 3, P::SL, P::NW>(sms, st, img, psf, out, N, C, H, W, c0);
-            } else {
-                if (alt) launch_gs<KS, 1, P::SL2, P::NW2>(sms, st, img, psf, out, N, C, H, W, c0);
-                else launch_gs<KS, 1, P::SL, P::NW>(sms, st, img, psf, out, N, C, H, W, c0);
+            if (plan < 0) {                                    // automatic: widest strips that cover W with <= 10 % padding
+                plan = 2;
+                for (int i = 0; i < 3; ++i) {
+                    const int spx = GSW_PX * StripPlan<KS>::P[i].U;
+                    if ((long long)((W + spx - 1) / spx) * spx * 10 <= (long long)W * 11 || StripPlan<KS>::P[i].U == 1) { plan = i; break; }
+                }
             }
+            if (plan == 1) launch_gs_plan<KS, 1>(cn, sms, st, img, psf, out, N, C, H, W, c0);
+            else if (plan == 2) launch_gs_plan<KS, 2>(cn, sms, st, img, psf, out, N, C, H, W, c0);
+            else launch_gs_plan<KS, 0>(cn, sms, st, img, psf, out, N, C, H, W, c0);
             return true;
         }
-        return launch_gs_ks<KS + 2>(ks, cn, alt, sms, st, img, psf, out, N, C, H, W, c0);
+        return launch_gs_ks<KS + 2>(ks, cn, plan, sms, st, img, psf, out, N, C, H, W, c0);
     }
 }
 
@@ -927,7 +940,7 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
         int c0 = 0;
         while (c0 < C) {
             const int cn = (C - c0 >= 3) ? 3 : 1;
-            if (!launch_gs_ks<3>(ks, cn, (dbg & 1024) != 0, sms, st, img, psf, out, N, C, H, W, c0))
+            if (!launch_gs_ks<3>(ks, cn, (dbg & 1024) ? 1 : (dbg & 4096) ? 2 : (dbg & 8192) ? 0 : -1, sms, st, img, psf, out, N, C, H, W, c0))
                 return fail(AADFF_E_INVALID, "unsupported kernel size");
             g_launches.fetch_add(1);
             CUDA_TRY(cudaGetLastError());
@@ -1037,6 +1050,7 @@ int aadff_thinlens_render_f32(const float* img, const float* depth, const float*
     const int tl_r = (ks - 1) / 2, tl_sh = (4 - tl_r % 4) % 4;
     const int tile_w = two_px ? TL2_TILE_W : TL_TILE_W;
     const long long tiles = (long long)N * ((H + TL_TILE_H - 1) / TL_TILE_H) * ((W + tile_w - 1) / tile_w);
+    if (tiles >= (1ll << 31)) return fail(AADFF_E_INVALID, "image batch too large for one launch");
     const int grid = (int)std::min<long long>(tiles, (long long)sms * 4);
     for (int c0 = 0; c0 < C; c0 += TL_MAXC) {
         a.c0 = c0;

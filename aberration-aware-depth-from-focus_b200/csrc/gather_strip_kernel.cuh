@@ -25,14 +25,17 @@
 
 namespace aadff {
 
-constexpr int GSW_PX = 64;                      // pixel columns per strip = 2 per lane
+constexpr int GSW_PX = 64;                      // pixel columns per pass over a strip row = 2 per lane
 
-template <int KS, int CN>
+// U = passes per strip row: the strip is 64*U columns wide and its row is still ONE bulk copy (small kernels: the
+// memory system likes long contiguous requests -- 12.5 KB chunks at ks = 7 reach 0.80 of the HBM peak, 25 KB ...)
+template <int KS, int CN, int U = 1>
 struct StripCfg {
     static constexpr int KK = KS * KS;
+    static constexpr int SPX = GSW_PX * U;                              // strip width
     static constexpr int HR = KS + 1;                                   // circular halo rows
-    static constexpr int PITCH = GSW_PX + KS - 1;                       // even
-    static constexpr int CHUNK_BYTES = GSW_PX * KK * 4;                 // multiple of 256
+    static constexpr int PITCH = SPX + KS - 1;                          // even
+    static constexpr int CHUNK_BYTES = SPX * KK * 4;                    // multiple of 256
     static constexpr int HALO_BYTES = ((HR * CN * PITCH * 4 + 127) / 128) * 128;
     __host__ __device__ static constexpr int WARP_BYTES(int sl) { return sl * CHUNK_BYTES + HALO_BYTES; }
     __host__ __device__ static constexpr int SMEM_BYTES(int sl, int nw) { return nw * WARP_BYTES(sl) + nw * sl * 8; }
@@ -44,12 +47,12 @@ __device__ __forceinline__ void cp_async_wait_group() {
     asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
 }
 
-template <int KS, int CN, int SL, int NW>
+template <int KS, int CN, int SL, int NW, int U = 1>
 __global__ void __launch_bounds__(NW * 32, 1)
 local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ psf, float* __restrict__ out,
                        int N, int C, int H, int W, int c0) {
-    using Cfg = StripCfg<KS, CN>;
-    constexpr int KK = Cfg::KK, R = (KS - 1) / 2, HR = Cfg::HR, PITCH = Cfg::PITCH;
+    using Cfg = StripCfg<KS, CN, U>;
+    constexpr int KK = Cfg::KK, R = (KS - 1) / 2, HR = Cfg::HR, PITCH = Cfg::PITCH, SPX = Cfg::SPX;
     constexpr int WB = Cfg::WARP_BYTES(SL);
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,7 +61,11 @@ local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ 
     const uint32_t bar0 = smem_u32(s_raw + NW * WB) + 8u * (uint32_t)(warp * SL);
     const uint32_t halo_u32 = smem_u32(s_halo);
 
-    const int nstrips = (W + GSW_PX - 1) / GSW_PX;
+    const int nstrips = (W + SPX - 1) / SPX;
+    // The flattened (image, strip, row) list is cut into one run per warp, balanced by ROWS: a warp's time per row is
+    // the latency of its chunk, not the chunk's width (balancing by pixels made the warps of a narrower last strip
+    // the slowest: measured 0.61 against 0.74 of the HBM peak at ks = 7, W = 640, 256-column strips) -- the host
+    // instead picks a strip width that divides W well.
     const long long RT = (long long)N * nstrips * H;                    // strip rows in the launch
     const long long TW = (long long)gridDim.x * NW, gw = (long long)blockIdx.x * NW + warp;
     const long long q0 = RT * gw / TW, q1 = RT * (gw + 1) / TW;
@@ -79,10 +86,10 @@ local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ 
         if (ip < nq) {
             if (lane == 0) {
                 const int slot = ip % SL;
-                const uint32_t bytes = (uint32_t)min(GSW_PX, W - GSW_PX * ps) * (uint32_t)(KK * 4);
+                const uint32_t bytes = (uint32_t)min(SPX, W - SPX * ps) * (uint32_t)(KK * 4);
                 mbar_arrive_expect_tx(bar0 + 8u * slot, bytes);
-                bulk_g2s(smem_u32(s_psf + slot * GSW_PX * KK),
-                         psf + ((long long)(pn * H + py) * W + GSW_PX * ps) * KK, bytes, bar0 + 8u * slot);
+                bulk_g2s(smem_u32(s_psf + slot * SPX * KK),
+                         psf + ((long long)(pn * H + py) * W + SPX * ps) * KK, bytes, bar0 + 8u * slot);
             }
             ++ip;
             if (++py == H) {
@@ -106,7 +113,7 @@ local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ 
 #pragma unroll
             for (int i0 = 0; i0 < PITCH; i0 += 32) {
                 const int i = i0 + lane;
-                if (i < PITCH) cp_async4(dst + 4u * i, src + min(max(GSW_PX * s - R + i, 0), W - 1));
+                if (i < PITCH) cp_async4(dst + 4u * i, src + min(max(SPX * s - R + i, 0), W - 1));
             }
         }
     };
@@ -130,50 +137,52 @@ local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ 
         mbar_wait(bar0 + 8u * slot, (uint32_t)((it / SL) & 1));
         __syncwarp();                                               // ... every lane's part
 
-        const int npx = min(GSW_PX, W - GSW_PX * s);
-        float acc[2][CN];
+        const int npx = min(SPX, W - SPX * s);
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {                               // 64 columns per pass
+            const int col = GSW_PX * u + 2 * lane;                  // this lane's first column inside the strip
+            float acc[2][CN];
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
-            for (int c = 0; c < CN; ++c) acc[p][c] = 0.f;
-        if (2 * lane < npx) {
-            const float2* tp = reinterpret_cast<const float2*>(s_psf + slot * GSW_PX * KK) + lane * KK;
+                for (int c = 0; c < CN; ++c) acc[p][c] = 0.f;
+            if (col < npx) {
+                const float2* tp = reinterpret_cast<const float2*>(s_psf + slot * SPX * KK) + (col >> 1) * KK;
 #pragma unroll
-            for (int dy = 0; dy < KS; ++dy) {
-                int hsl = hs + dy;
-                hsl -= (hsl >= HR) ? HR : 0;
-                const float2* hrow = reinterpret_cast<const float2*>(s_halo + hsl * CN * PITCH) + lane;
-                float win[CN][KS + 1];
+                for (int dy = 0; dy < KS; ++dy) {
+                    int hsl = hs + dy;
+                    hsl -= (hsl >= HR) ? HR : 0;
+                    const float2* hrow = reinterpret_cast<const float2*>(s_halo + hsl * CN * PITCH) + (col >> 1);
+                    float win[CN][KS + 1];
 #pragma unroll
-                for (int c = 0; c < CN; ++c)
+                    for (int c = 0; c < CN; ++c)
 #pragma unroll
-                    for (int i = 0; i < (KS + 1) / 2; ++i) {
-                        const float2 v = hrow[c * (PITCH / 2) + i];
-                        win[c][2 * i] = v.x;
-                        win[c][2 * i + 1] = v.y;
-                    }
+                        for (int i = 0; i < (KS + 1) / 2; ++i) {
+                            const float2 v = hrow[c * (PITCH / 2) + i];
+                            win[c][2 * i] = v.x;
+                            win[c][2 * i + 1] = v.y;
+                        }
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    const int e0 = p * KK + dy * KS;                // compile-time after unrolling
+                    for (int p = 0; p < 2; ++p) {
+                        const int e0 = p * KK + dy * KS;            // compile-time after unrolling
 #pragma unroll
-                    for (int dx = 0; dx < KS; ++dx) {
-                        const int e = e0 + dx;
-                        const float2 tv = tp[e >> 1];
-                        const float t = (e & 1) ? tv.y : tv.x;
+                        for (int dx = 0; dx < KS; ++dx) {
+                            const int e = e0 + dx;
+                            const float2 tv = tp[e >> 1];
+                            const float t = (e & 1) ? tv.y : tv.x;
 #pragma unroll
-                        for (int c = 0; c < CN; ++c) acc[p][c] = fmaf(win[c][p + dx], t, acc[p][c]);
+                            for (int c = 0; c < CN; ++c) acc[p][c] = fmaf(win[c][p + dx], t, acc[p][c]);
+                        }
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < CN; ++c)
+                    *reinterpret_cast<float2*>(out + ((long long)(n * C + c0 + c) * H + y) * W + SPX * s + col) =
+                        make_float2(acc[0][c], acc[1][c]);
             }
         }
         __syncwarp();                                               // every lane is done with the chunk and row y-R
         issue_chunk();                                              // refill this slot (chunk q + SL)
-        if (2 * lane < npx) {
-#pragma unroll
-            for (int c = 0; c < CN; ++c)
-                *reinterpret_cast<float2*>(out + ((long long)(n * C + c0 + c) * H + y) * W + GSW_PX * s + 2 * lane) =
-                    make_float2(acc[0][c], acc[1][c]);
-        }
         if (++y == H) {
             y = 0;
             fresh = true;

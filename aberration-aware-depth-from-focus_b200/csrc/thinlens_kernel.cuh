@@ -216,6 +216,12 @@ thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap
 // CTA tile = 8 rows x 64 columns (warp = row, lane j = columns 2j, 2j+1); halo staging (TMA box / clamped cp.async,
 // double-buffered) as above.  ~5 instead of ~9 instructions per tap and pixel.
 constexpr int TL2_TILE_W = 64;
+#ifndef AADFF_TL2_MINB
+#define AADFF_TL2_MINB 1          // resident CTAs per SM the register allocation aims at
+#endif
+#ifndef AADFF_TL2_UNROLL_SIDE
+#define AADFF_TL2_UNROLL_SIDE 1   // 1: rows -dy and +dy as straight-line code (windows of one under the FFMAs of the other)
+#endif
 
 template <int KS>
 struct ThinLens2Cfg {
@@ -233,7 +239,7 @@ struct ThinLens2Cfg {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(TL_NT)
+__global__ void __launch_bounds__(TL_NT, AADFF_TL2_MINB)
 thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap img_map) {
     using Cfg = ThinLens2Cfg<KS>;
     constexpr int R = Cfg::R, HH = Cfg::HH, HW = Cfg::HW, BW = Cfg::BW, SH = Cfg::SH, CSTRIDE = Cfg::CSTRIDE;
@@ -243,7 +249,7 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
     const uint32_t bar0 = smem_u32(tl_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (a.W + TL2_TILE_W - 1) / TL2_TILE_W, tiles_y = (a.H + TL_TILE_H - 1) / TL_TILE_H;
-    const long long n_tiles = (long long)a.N * tiles_x * tiles_y;
+    const int n_tiles = a.N * tiles_x * tiles_y;               // < 2^31 (checked by the host): 32-bit tile arithmetic
     const bool flip = a.flip_dev ? (*a.flip_dev != 0) : (a.flip != 0);
     const int buf_floats = Cfg::BUF_FLOATS(a.cn);
 
@@ -254,16 +260,16 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
     }
     __syncthreads();
 
-    auto coords = [&](long long tile, int& n, int& h0, int& w0) {
-        const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
-        n = (int)(tile / ((long long)tiles_x * tiles_y));
-        h0 = ty * TL_TILE_H;
+    auto coords = [&](int tile, int& n, int& h0, int& w0) {
+        const int row = tile / tiles_x, tx = tile - row * tiles_x;
+        n = row / tiles_y;
+        h0 = (row - n * tiles_y) * TL_TILE_H;
         w0 = tx * TL2_TILE_W;
     };
     auto interior = [&](int h0, int w0) {      // the halo lies inside the image (the box's alignment / spare columns may not: unused)
         return a.use_tma && h0 - R >= 0 && w0 - R >= 0 && h0 - R + HH <= a.H && w0 - R + HW <= a.W;
     };
-    auto issue_halo = [&](long long tile, int b) {
+    auto issue_halo = [&](int tile, int b) {
         int n, h0, w0;
         coords(tile, n, h0, w0);
         float* dst = bufs + b * buf_floats;
@@ -273,13 +279,23 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                 tma_load_3d(smem_u32(dst), &img_map, w0 - R - SH, h0 - R, n * a.C + a.c0, bar0 + 8 * b);
             }
         } else {
-            const uint32_t d0 = smem_u32(dst);
-            for (int idx = threadIdx.x; idx < a.cn * HH * HW; idx += TL_NT) {
-                const int c = idx / (HH * HW), rem = idx - c * (HH * HW);
-                const int yy = rem / HW, xx = rem - yy * HW;
-                const int gy = min(max(h0 + yy - R, 0), a.H - 1), gx = min(max(w0 + xx - R, 0), a.W - 1);   // replicate
-                cp_async4(d0 + 4u * (uint32_t)(c * CSTRIDE + yy * BW + xx + SH),
-                          a.img + ((long long)(n * a.C + a.c0 + c) * a.H + gy) * a.W + gx);
+            // warp = halo row (stride 8), lane = halo column (stride 32): no index divisions
+            const uint32_t d0 = smem_u32(dst) + 4u * (uint32_t)SH;
+            const float* plane0 = a.img + (long long)(n * a.C + a.c0) * a.H * a.W;
+            const long long plane = (long long)a.H * a.W;
+            for (int yy = warp; yy < HH; yy += TL_TILE_H) {
+                const int gy = min(max(h0 + yy - R, 0), a.H - 1);                                   // replicate
+#pragma unroll
+                for (int x0 = 0; x0 < HW; x0 += 32) {
+                    const int xx = x0 + lane;
+                    if (xx < HW) {
+                        const float* src = plane0 + (long long)gy * a.W + min(max(w0 + xx - R, 0), a.W - 1);
+                        const uint32_t d = d0 + 4u * (uint32_t)(yy * BW + xx);
+                        cp_async4(d, src);
+                        if (a.cn > 1) cp_async4(d + 4u * CSTRIDE, src + plane);
+                        if (a.cn > 2) cp_async4(d + 8u * CSTRIDE, src + 2 * plane);
+                    }
+                }
             }
         }
     };
@@ -287,8 +303,8 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
     constexpr bool DB = Cfg::NBUF == 2;
     uint32_t phase = 0;
     int cur = 0;
-    if (DB && (long long)blockIdx.x < n_tiles) issue_halo(blockIdx.x, 0);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (DB && (int)blockIdx.x < n_tiles) issue_halo(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int n, h0, w0;
         coords(tile, n, h0, w0);
         const int h = h0 + warp, w = w0 + 2 * lane;
@@ -324,7 +340,7 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
             cp_async_wait_all();
         }
         __syncthreads();
-        if (DB && tile + gridDim.x < n_tiles) issue_halo(tile + gridDim.x, cur ^ 1);
+        if (DB && tile + (int)gridDim.x < n_tiles) issue_halo(tile + gridDim.x, cur ^ 1);
 
         if (ok[0]) {
             float g[2][R + 1];                                  // g[p][d] = 2^(d^2 cexp): the separable Gaussian factor
@@ -357,7 +373,11 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                     rs = fmaf(2.f, rs, wt[p][0]);
                     wsum[p] += (da == 0) ? rs : 2.f * rs;
                 }
+#if AADFF_TL2_UNROLL_SIDE
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                 for (int side = 0; side < 2; ++side) {
                     if (side == 1 && da == 0) break;
                     const int i = side ? R + da : R - da;

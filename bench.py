@@ -421,6 +421,50 @@ def c5_training_step(aadff_b200, lens, batches, n_steps=3):
     return out
 
 
+def secondary_kernels(aadff_b200, flush, peak_hbm):
+    """The HBM-bound kernels of the path's neighbours, one line each (median of 7 launches, L2 flushed before each):
+    local_psf_render alone on a PSF tensor in HBM (algorithmic bytes = 4 k^2 + 24 per pixel at C = 3) and the fused
+    thin-lens render (28 B per pixel: far from HBM-bound, reported in Gpix/s)."""
+    import torch
+    ThinLens = aadff_b200.ThinLens
+
+    def median_ms(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    res = {}
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for ks, n in ((11, 16), (31, 4)):
+        img = torch.rand(n, 3, 512, 512, device="cuda", generator=g)
+        psf = torch.rand(n, 512, 512, ks, ks, device="cuda", generator=g)
+        ms = median_ms(lambda: aadff_b200.local_psf_render(img, psf, ks))
+        gbs = n * 512 * 512 * (4 * ks * ks + 24) / ms / 1e6
+        res[f"local_psf_render_k{ks}"] = {
+            "shape": [n, 3, 512, 512], "ms": ms, "Gpix_per_s": n * 512 * 512 / ms / 1e6,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm},
+            "kernel": "local_psf_strip_kernel" if ks <= 15 else "local_psf_coalesced_kernel"}
+        del img, psf
+    tl = ThinLens(foc_len=50.0, fnum=1.8, kernel_size=11, sensor_size=[36.0, 24.0], sensor_res=(512, 512)).to("cuda")
+    img = torch.rand(16, 3, 512, 512, device="cuda", generator=g)
+    dep = -(300 + 5000 * torch.rand(16, 1, 512, 512, device="cuda", generator=g))
+    foc = -(500 + 3000 * torch.rand(16, device="cuda", generator=g))
+    ms = median_ms(lambda: tl.render(img, dep, foc))
+    res["thinlens_render_k11"] = {"shape": [16, 3, 512, 512], "ms": ms, "Gpix_per_s": 16 * 512 * 512 / ms / 1e6,
+                                  "T_taps_per_s": 16 * 512 * 512 * 121 / ms / 1e9, "bound": "issue (FFMA + LDS per tap)",
+                                  "kernel": "thinlens_render2_kernel"}
+    return res
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -515,6 +559,12 @@ def run_ours(args):
         for mode in [m for m in ("econ", "fast", "mixed") if m != args.mode]:
             tt, _ = timed(mode, max(3, args.steps // 2), 2)
             extra[mode] = {"value": units / (statistics.mean(tt) * 1e-3) / 1e6, "unit": UNIT, "dtype": DTYPES[mode]}
+    secondary = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            secondary = secondary_kernels(aadff_b200, flush, load_peaks()[2])
+        except Exception as e:                                   # never lose the headline line over a side measurement
+            secondary = {"error": repr(e)}
 
     if rank == 0:
         peak_tf, peak_tf_sus, peak_hbm, peak_src = load_peaks()
@@ -555,6 +605,8 @@ def run_ours(args):
             line["strong"] = strong
         if extra:
             line["other_modes"] = extra
+        if secondary:
+            line["secondary_kernels"] = secondary
         if world == 1 and not args.no_cpu:
             del flush
             torch.cuda.empty_cache()

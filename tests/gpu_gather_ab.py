@@ -1,5 +1,5 @@
 """A/B timing of the stand-alone gather kernels: python tests/gpu_gather_ab.py [N H W]
-flags 0 = strip-walking kernel (ks <= 15), 1024 = its deeper-ring variant, 512 = register-streaming kernel.
+flags 0 = strip-walking kernel (ks <= 15), 8192 / 1024 / 4096 = its shared-memory plans 0 / 1 / 2 forced (0 = automatic choice), 512 = register-streaming kernel.
 Prints algorithmic GB/s (4 ks^2 + 24 B per pixel at C = 3) and the fraction of the measured HBM peak."""
 import json
 import os
@@ -26,7 +26,7 @@ for ks in (3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 31):
     img = torch.rand(n, 3, H, W, device="cuda")
     psf = torch.rand(n, H, W, ks, ks, device="cuda")
     ref = None
-    for flags in ((512, 0, 1024) if ks <= 15 else (512,)):
+    for flags in ((512, 0, 8192, 1024, 4096) if ks <= 15 else (512,)):
         lib.aadff_debug_set_flags(flags)
         for _ in range(3):
             out = aadff_b200.local_psf_render(img, psf, ks)

@@ -121,16 +121,17 @@ def test_gather_every_kernel_size_vs_oracle(pkg, ks):
 def test_gather_strip_kernel_vs_oracle_and_register_streaming(pkg, ks):
     """Strip-walking gather (gather_strip_kernel.cuh; taken when W % 4 == 0 and ks <= 15; larger ks exercise the fall-through): partial strips (W = 68, 132,
     200), a strip narrower than one lane pair (W = 4), images shorter than the kernel (H = 3), several images / strips
-    per warp run, C = 1 / 3 / 4, both shared-memory plans (debug flag 1024 = deeper ring), against the oracle's direct
-    definition and against the register-streaming kernel (debug flag 512)."""
+    per warp run, C = 1 / 3 / 4, the automatic plan and all three shared-memory plans forced (debug flags 8192 / 1024 / 4096: strips of 64 - 256
+    columns taken in 64-column passes, deeper rings), against the oracle's direct definition and against the register-streaming
+    kernel (debug flag 512)."""
     from deeplens.render_psf import local_psf_render
     gen = torch.Generator().manual_seed(300 + ks)
-    for (N, C, H, W) in [(2, 3, 19, 68), (1, 4, 33, 132), (1, 1, 3, 4), (1, 3, 70, 64), (3, 3, 9, 200)]:
+    for (N, C, H, W) in [(2, 3, 19, 68), (1, 4, 33, 132), (1, 1, 3, 4), (1, 3, 70, 64), (3, 3, 9, 200), (1, 3, 12, 332)]:
         img = torch.rand(N, C, H, W, generator=gen)
         psf = torch.rand(N, H, W, ks, ks, generator=gen)
         psf = psf / psf.sum((-1, -2), keepdim=True)
         ref = orc.local_psf_render(img, psf, ks)
-        for flags in (0, 1024, 512):
+        for flags in (0, 8192, 1024, 4096, 512):
             pkg.native.lib.aadff_debug_set_flags(flags)
             try:
                 out = local_psf_render(img.cuda(), psf.cuda(), ks)
