@@ -68,54 +68,56 @@ bool launch_gather_coalesced(int ks, int cn, int grid, cudaStream_t st, const fl
     return launch_gc_ks<3>(ks, cn, grid, st, img, psf, out, N, C, H, W, c0);
 }
 
-// Strip-walking gather (gather_strip_kernel.cuh), ks <= 15: slots per warp (SL) / warps per CTA (NW) / 64-column
-// passes per strip row (U) chosen so that the PSF slots and the per-warp halo rings fill the 227 KB of shared memory.
+// Strip-walking gather (gather_strip_kernel.cuh), ks <= 15: slots per warp (SL) / warps per CTA (NW) / strip width
+// (SPX: 32, 64, or 64 U taken in U passes) chosen so that the PSF slots and the per-warp halo rings fill the 227 KB of shared memory.
 // Plans are ordered widest strip first: the memory system likes long contiguous requests (ks = 7: 12.5 KB chunks reach
 // 0.79 of the HBM peak, 25 KB 0.84, 50 KB 0.88), but a strip width that does not divide W wastes the narrower last
 // strip (a chunk costs its latency, whatever its width): the first plan whose strips cover W with <= 10 % of padding
 // runs.  Debug flags 1024 / 4096 force plan 1 / 2 (A/B timing).
-struct StripShape { int SL, NW, U; };
+struct StripShape { int SL, NW, SPX; };
 template <int KS> struct StripPlan;
-template <> struct StripPlan<3>  { static constexpr StripShape P[3] = {{2, 7, 4}, {2, 12, 2}, {4, 16, 1}}; };
-template <> struct StripPlan<5>  { static constexpr StripShape P[3] = {{1, 5, 4}, {2, 6, 2}, {2, 12, 1}}; };
-template <> struct StripPlan<7>  { static constexpr StripShape P[3] = {{1, 3, 4}, {1, 6, 2}, {1, 11, 1}}; };
-template <> struct StripPlan<9>  { static constexpr StripShape P[3] = {{1, 3, 2}, {1, 7, 1}, {2, 4, 1}}; };
-template <> struct StripPlan<11> { static constexpr StripShape P[3] = {{1, 5, 1}, {2, 3, 1}, {2, 3, 1}}; };
-template <> struct StripPlan<13> { static constexpr StripShape P[3] = {{2, 2, 1}, {1, 4, 1}, {1, 4, 1}}; };
-template <> struct StripPlan<15> { static constexpr StripShape P[3] = {{1, 3, 1}, {3, 1, 1}, {3, 1, 1}}; };
-// ks = 17 / 19 fit two warps only and measured 0.61 / 0.63 of the HBM peak against 0.72 / 0.78 for the
-// register-streaming kernel: the strip kernel stops at 15 (0.83 against 0.71).
+template <> struct StripPlan<3>  { static constexpr StripShape P[3] = {{2, 7, 256}, {2, 12, 128}, {4, 16, 64}}; };
+template <> struct StripPlan<5>  { static constexpr StripShape P[3] = {{1, 5, 256}, {2, 6, 128}, {2, 12, 64}}; };
+template <> struct StripPlan<7>  { static constexpr StripShape P[3] = {{1, 3, 256}, {1, 6, 128}, {1, 11, 64}}; };
+template <> struct StripPlan<9>  { static constexpr StripShape P[3] = {{1, 3, 128}, {1, 7, 64}, {2, 4, 64}}; };
+template <> struct StripPlan<11> { static constexpr StripShape P[3] = {{1, 5, 64}, {2, 3, 64}, {2, 3, 64}}; };
+template <> struct StripPlan<13> { static constexpr StripShape P[3] = {{2, 2, 64}, {1, 4, 64}, {1, 4, 64}}; };
+template <> struct StripPlan<15> { static constexpr StripShape P[3] = {{1, 3, 64}, {3, 1, 64}, {3, 1, 64}}; };
+// Beyond 15 a 64-column chunk plus its halo ring fits only twice (measured 0.61 / 0.63 of the HBM peak at ks = 17 / 19
+// against 0.72 / 0.78 for the register-streaming kernel), and 32-column strips (sixteen lanes of each warp idle, three
+// or four warps) are bound by the warps' own arithmetic: 0.58 / 0.48 / 0.49 / 0.35 at ks = 17 / 19 / 21 / 23.
+constexpr int STRIP_MAX_KS = 15;
 
-template <int KS, int CN, int SL, int NW, int U>
+template <int KS, int CN, int SL, int NW, int SPX>
 void launch_gs(int sms, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H, int W,
                int c0) {
-    constexpr int smem = StripCfg<KS, CN, U>::SMEM_BYTES(SL, NW);
+    constexpr int smem = StripCfg<KS, CN, SPX>::SMEM_BYTES(SL, NW);
     static_assert(smem <= 232448, "strip gather: shared memory plan does not fit");
     if (smem > 48 * 1024)      // per-device attribute: set on every launch that needs the opt-in
-        cudaFuncSetAttribute(local_psf_strip_kernel<KS, CN, SL, NW, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const long long rows = (long long)N * ((W + GSW_PX * U - 1) / (GSW_PX * U)) * H;
+        cudaFuncSetAttribute(local_psf_strip_kernel<KS, CN, SL, NW, SPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const long long rows = (long long)N * ((W + SPX - 1) / SPX) * H;
     const int grid = (int)std::min<long long>((rows + NW - 1) / NW, sms);
-    local_psf_strip_kernel<KS, CN, SL, NW, U><<<grid, NW * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
+    local_psf_strip_kernel<KS, CN, SL, NW, SPX><<<grid, NW * 32, smem, st>>>(img, psf, out, N, C, H, W, c0);
 }
 template <int KS, int I>
 void launch_gs_plan(int cn, int sms, cudaStream_t st, const float* img, const float* psf, float* out, int N, int C, int H,
                     int W, int c0) {
     constexpr StripShape S = StripPlan<KS>::P[I];
-    if (cn == 3) launch_gs<KS, 3, S.SL, S.NW, S.U>(sms, st, img, psf, out, N, C, H, W, c0);
-    else launch_gs<KS, 1, S.SL, S.NW, S.U>(sms, st, img, psf, out, N, C, H, W, c0);
+    if (cn == 3) launch_gs<KS, 3, S.SL, S.NW, S.SPX>(sms, st, img, psf, out, N, C, H, W, c0);
+    else launch_gs<KS, 1, S.SL, S.NW, S.SPX>(sms, st, img, psf, out, N, C, H, W, c0);
 }
 template <int KS>
 bool launch_gs_ks(int ks, int cn, int plan, int sms, cudaStream_t st, const float* img, const float* psf, float* out,
                   int N, int C, int H, int W, int c0) {
-    if constexpr (KS > 15) {
+    if constexpr (KS > STRIP_MAX_KS) {
         return false;
     } else {
         if (ks == KS) {
             if (plan < 0) {                                    // automatic: widest strips that cover W with <= 10 % padding
                 plan = 2;
                 for (int i = 0; i < 3; ++i) {
-                    const int spx = GSW_PX * StripPlan<KS>::P[i].U;
-                    if ((long long)((W + spx - 1) / spx) * spx * 10 <= (long long)W * 11 || StripPlan<KS>::P[i].U == 1) { plan = i; break; }
+                    const int spx = StripPlan<KS>::P[i].SPX;
+                    if ((long long)((W + spx - 1) / spx) * spx * 10 <= (long long)W * 11 || spx <= GSW_PX) { plan = i; break; }
                 }
             }
             if (plan == 1) launch_gs_plan<KS, 1>(cn, sms, st, img, psf, out, N, C, H, W, c0);
@@ -934,8 +936,8 @@ int aadff_local_psf_render_f32(const float* img, const float* psf, float* out, i
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int dbg = g_dbg_flags.load();
-    if (ks >= 3 && ks <= 15 && !(dbg & (128 | 512)) && W % 4 == 0 && reinterpret_cast<uintptr_t>(psf) % 16 == 0 &&
-        reinterpret_cast<uintptr_t>(out) % 8 == 0 && (long long)N * H * ((W + GSW_PX - 1) / GSW_PX) < (1ll << 40)) {
+    if (ks >= 3 && ks <= STRIP_MAX_KS && !(dbg & (128 | 512)) && W % 4 == 0 && reinterpret_cast<uintptr_t>(psf) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 8 == 0 && (long long)N * H * ((W + 31) / 32) < (1ll << 40)) {
         // strip-walking kernel (gather_strip_kernel.cuh): bulk-copied PSF rows, per-warp pipelines
         int c0 = 0;
         while (c0 < C) {

@@ -1,4 +1,4 @@
-// Stand-alone per-pixel PSF gather, strip-walking version for small and medium kernels (ks <= 15): the CUDA
+// Stand-alone per-pixel PSF gather, strip-walking version for ks <= 15: the CUDA
 // counterpart of deeplens/render_psf.py:76-107 (local_psf_render) for a PSF tensor in HBM ([N,H,W,ks,ks] fp32).
 //
 // The register-streaming kernel (gather_coalesced_kernel.cuh) spends ~83 warp instructions per pixel at ks = 11
@@ -17,8 +17,7 @@
 //   * the flattened list of (image, strip, row) is cut into one contiguous run per warp (balanced to +-1 row), so
 //     there is no work counter and no tail.
 // Requirements (else the host falls back to the register-streaming kernel): W % 4 == 0, 16-byte aligned psf,
-// 8-byte aligned out, ks odd in 3..15 (beyond that fewer than three warps' chunks fit into shared memory and the register-
-// streaming kernel is faster: measured 0.61 against 0.72 of the HBM peak at ks = 17).
+// 8-byte aligned out, ks odd in 3..15 (larger kernels: see StripPlan in aadff_api.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include "ptx_sm100.cuh"
@@ -27,12 +26,14 @@ namespace aadff {
 
 constexpr int GSW_PX = 64;                      // pixel columns per pass over a strip row = 2 per lane
 
-// U = passes per strip row: the strip is 64*U columns wide and its row is still ONE bulk copy (small kernels: the
-// memory system likes long contiguous requests -- 12.5 KB chunks at ks = 7 reach 0.80 of the HBM peak, 25 KB ...)
-template <int KS, int CN, int U = 1>
+// SPX = strip width: 64, or 64*U taken in U passes over ONE bulk copy (small kernels: the memory system likes long contiguous requests --
+// 12.5 KB chunks at ks = 7 reach 0.79 of the HBM peak, 25 KB 0.84, 50 KB 0.87)
+template <int KS, int CN, int SPX_ = GSW_PX>
 struct StripCfg {
     static constexpr int KK = KS * KS;
-    static constexpr int SPX = GSW_PX * U;                              // strip width
+    static constexpr int SPX = SPX_;                                    // strip width
+    static constexpr int U = (SPX + GSW_PX - 1) / GSW_PX;               // 64-column passes per strip row
+    static_assert(SPX % 32 == 0, "strip width");
     static constexpr int HR = KS + 1;                                   // circular halo rows
     static constexpr int PITCH = SPX + KS - 1;                          // even
     static constexpr int CHUNK_BYTES = SPX * KK * 4;                    // multiple of 256
@@ -47,12 +48,12 @@ __device__ __forceinline__ void cp_async_wait_group() {
     asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory");
 }
 
-template <int KS, int CN, int SL, int NW, int U = 1>
+template <int KS, int CN, int SL, int NW, int SPX_ = GSW_PX>
 __global__ void __launch_bounds__(NW * 32, 1)
 local_psf_strip_kernel(const float* __restrict__ img, const float* __restrict__ psf, float* __restrict__ out,
                        int N, int C, int H, int W, int c0) {
-    using Cfg = StripCfg<KS, CN, U>;
-    constexpr int KK = Cfg::KK, R = (KS - 1) / 2, HR = Cfg::HR, PITCH = Cfg::PITCH, SPX = Cfg::SPX;
+    using Cfg = StripCfg<KS, CN, SPX_>;
+    constexpr int KK = Cfg::KK, R = (KS - 1) / 2, HR = Cfg::HR, PITCH = Cfg::PITCH, SPX = Cfg::SPX, U = Cfg::U;
     constexpr int WB = Cfg::WARP_BYTES(SL);
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

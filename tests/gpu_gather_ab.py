@@ -19,7 +19,7 @@ except Exception:
     pass
 lib = aadff_b200.native.lib
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for ks in (3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 31):
+for ks in (3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 31):
     n = N if ks <= 13 else max(1, N // 4)
     if len(sys.argv) > 4 and str(ks) not in sys.argv[4].split(','):
         continue
