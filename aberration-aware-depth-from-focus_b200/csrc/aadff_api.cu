@@ -23,6 +23,7 @@
 #include "psf_conv_kernel.cuh"
 #include "train_kernels.cuh"
 #include "preprocess_kernel.cuh"
+#include "spline_rotate_kernel.cuh"
 #include "econ_calib.h"
 
 using namespace aadff;
@@ -1113,11 +1114,71 @@ int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* a
     if (depth_mode != 0 && depth_mode != 1) return fail(AADFF_E_INVALID, "depth_mode must be 0 (antialias) or 1 (cv2 linear)");
     if (B == 0) return AADFF_OK;
     PreprocessArgs a{};
-    a.bgr = bgr; a.depth = depth; a.aif_out = aif_out; a.depth_out = depth_out; a.jitter = jitter; a.flips = flips;
+    a.bgr = bgr; a.depth = depth; a.aif_out = bgr ? aif_out : nullptr; a.depth_out = depth ? depth_out : nullptr;
+    a.jitter = jitter; a.flips = flips;
     a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.depth_div = depth_div; a.depth_mode = depth_mode;
     const long long per_image = (long long)h * w;
     const dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 148 * 16), (unsigned)B);
     if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
+    preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_prepare_planes_u8(const uint8_t* bgr, const uint16_t* depth, float* planes, int B, int H, int W, float depth_div,
+                            const float* jitter, const uint8_t* flips, void* stream) {
+    if ((!bgr && !depth) || !planes) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (depth && !(depth_div > 0.f)) return fail(AADFF_E_INVALID, "depth divisor must be positive");
+    if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
+    if (B == 0) return AADFF_OK;
+    PlanesArgs a{};
+    a.bgr = bgr; a.depth = depth; a.planes = planes; a.jitter = jitter; a.flips = flips;
+    a.B = B; a.H = H; a.W = W; a.P = (bgr ? 3 : 0) + (depth ? 1 : 0); a.depth_div = depth_div;
+    const dim3 grid((unsigned)std::min<long long>(((long long)H * W + 255) / 256, 148 * 8), (unsigned)B);
+    prepare_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_spline_affine_f32(const float* planes, float* work, float* out, int B, int P, int H, int W, const double* xform,
+                            int clamp_plane, void* stream) {
+    if (!planes || !work || !out || !xform) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || P < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (clamp_plane >= P) return fail(AADFF_E_INVALID, "clamp_plane out of range");
+    if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
+    if (B == 0) return AADFF_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)B * P * H * W;
+    float* tmp = work;                 // prefiltered along W
+    float* coef = work + n;            // ... and along H
+    const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
+    spline_prefilter_kernel<1><<<blocks, 256, 0, st>>>(planes, tmp, (long long)B * P, H, W);
+    spline_prefilter_kernel<0><<<blocks, 256, 0, st>>>(tmp, coef, (long long)B * P, H, W);
+    AffineArgs a{};
+    a.coef = coef; a.raw = planes; a.out = out; a.xform = xform; a.B = B; a.P = P; a.H = H; a.W = W; a.clamp_plane = clamp_plane;
+    const dim3 grid((unsigned)std::min<long long>(((long long)H * W + 255) / 256, 148 * 8), (unsigned)B);
+    spline_affine_kernel<<<grid, 256, 0, st>>>(a);
+    g_launches.fetch_add(3);
+    CUDA_TRY(cudaGetLastError());
+    return AADFF_OK;
+}
+
+int aadff_resize_planes_f32(const float* planes, float* aif_out, float* depth_out, int B, int P, int H, int W, int h, int w,
+                            int depth_mode, void* stream) {
+    if (!planes || (!aif_out && !depth_out)) return fail(AADFF_E_INVALID, "null argument");
+    if (B < 0 || H < 1 || W < 1 || h < 1 || w < 1) return fail(AADFF_E_INVALID, "bad shape");
+    if (P != (aif_out ? 3 : 0) + (depth_out ? 1 : 0)) return fail(AADFF_E_INVALID, "P must be 3 (image), 1 (depth) or 4 (both)");
+    if (depth_mode != 0 && depth_mode != 1) return fail(AADFF_E_INVALID, "depth_mode must be 0 (antialias) or 1 (cv2 linear)");
+    if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
+    if (B == 0) return AADFF_OK;
+    PreprocessArgs a{};
+    a.aif_out = aif_out; a.depth_out = depth_out; a.fsrc = planes; a.fsrc_planes = P; a.fsrc_depth_plane = P - 1;
+    a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.depth_div = 1.f; a.depth_mode = depth_mode;
+    const long long per_image = (long long)h * w;
+    const dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 148 * 16), (unsigned)B);
     preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());

@@ -11,8 +11,8 @@
 //
 // One thread per output pixel; the separable filter weights are evaluated on the fly (a 1280x1024 -> 640x480 resize
 // touches 5 x 5 inputs per output).  HBM traffic: 5 B per input pixel + 16 B per output pixel.  The spline rotation of
-// AutoAgument (scipy.ndimage.rotate, order 3) is NOT rebuilt: it needs a global prefilter pass; callers that want it
-// apply it before upload.
+// AutoAgument (scipy.ndimage.rotate, order 3) needs a global prefilter pass: spline_rotate_kernel.cuh produces rotated
+// full-resolution fp32 planes, which this kernel resizes through its `fsrc` source.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -29,6 +29,10 @@ struct PreprocessArgs {
     int B, H, W, h, w;
     float depth_div;
     int depth_mode;           // 0: antialiased bilinear (torchvision Resize), 1: cv2 INTER_LINEAR
+    // alternative source: fp32 planes [B,P,H,W] at full resolution (RGB planes first, then depth) that already carry
+    // jitter / flips / rotation (spline_rotate_kernel.cuh); aif_out / depth_out say which outputs are wanted
+    const float* fsrc;
+    int fsrc_planes, fsrc_depth_plane;
 };
 
 // ATen's antialiased linear filter along one axis: window [lo, lo+n) of input samples and normalisation for output i
@@ -63,8 +67,10 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
     const long long total = (long long)a.h * a.w;
     for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(id % a.w), oy = (int)(id / a.w);
-        const int fl = a.flips ? a.flips[b] : 0;
+        const int fl = (a.flips && !a.fsrc) ? a.flips[b] : 0;
         const bool flx = fl & 1, fly = fl & 2;
+        const long long fplane = (long long)a.H * a.W;
+        const float* fs = a.fsrc ? a.fsrc + (long long)b * a.fsrc_planes * fplane : nullptr;
         int ylo, yn, xlo, xn;
         float yc, yinv, xc, xinv;
         aa_window(oy, a.H, a.h, ylo, yn, yc, yinv);
@@ -77,18 +83,24 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
 #pragma unroll
         for (int j = 0; j < PP_MAXW; ++j) wxs[j] = (j < xn) ? aa_weight(j, xlo, xc, xinv) / wxsum : 0.f;
         auto wx_of = [&](int j) { return (xn <= PP_MAXW) ? wxs[j] : aa_weight(j, xlo, xc, xinv) / wxsum; };
-        if (a.bgr) {
+        if (a.aif_out) {
             float acc[3] = {0.f, 0.f, 0.f};
             for (int jy = 0; jy < yn; ++jy) {
                 const float wy = aa_weight(jy, ylo, yc, yinv) / wysum;
                 const int sy = fly ? a.H - 1 - (ylo + jy) : ylo + jy;             // the flip precedes the resize
                 const uint8_t* row = a.bgr + ((long long)b * a.H + sy) * a.W * 3;
+                const float* frow = fs + (long long)sy * a.W;
                 float racc[3] = {0.f, 0.f, 0.f};
                 auto tap = [&](int jx, float wx) {
                     const int sx = flx ? a.W - 1 - (xlo + jx) : xlo + jx;
-                    const uint8_t* px = row + sx * 3;
+                    if (fs) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) racc[c] = fmaf(wx, lut[px[2 - c]], racc[c]);   // BGR -> RGB, /255, jitter
+                        for (int c = 0; c < 3; ++c) racc[c] = fmaf(wx, frow[c * fplane + sx], racc[c]);
+                    } else {
+                        const uint8_t* px = row + sx * 3;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) racc[c] = fmaf(wx, lut[px[2 - c]], racc[c]);   // BGR -> RGB, /255, jitter
+                    }
                 };
                 if (xn <= PP_MAXW) {
 #pragma unroll
@@ -103,9 +115,11 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
 #pragma unroll
             for (int c = 0; c < 3; ++c) a.aif_out[(((long long)b * 3 + c) * a.h + oy) * a.w + ox] = acc[c];
         }
-        if (a.depth) {
+        if (a.depth_out) {
             const uint16_t* dp = a.depth + (long long)b * a.H * a.W;
+            const float* fd = fs + (long long)a.fsrc_depth_plane * fplane;
             auto at = [&](int sy, int sx) {
+                if (fs) return fd[(long long)sy * a.W + sx];
                 sy = fly ? a.H - 1 - sy : sy;
                 sx = flx ? a.W - 1 - sx : sx;
                 return (float)dp[(long long)sy * a.W + sx] / a.depth_div;

@@ -124,10 +124,28 @@ int aadff_render_psf_map_f32(const float* img, const float* psf_map, float* out,
  * uint16 depth / depth_div (-> flips) -> the same resize (depth_mode 0) or cv2.resize INTER_LINEAR (depth_mode 1).
  *   bgr [B,H,W,3] uint8, depth [B,H,W] uint16 (either may be NULL), aif_out [B,3,h,w], depth_out [B,1,h,w] fp32;
  *   jitter [B,2] = (contrast, brightness) per image, contrast < 0 = no jitter, or NULL; flips [B]: bit 0 horizontal,
- *   bit 1 vertical, or NULL.  Device pointers, stream-ordered.  AutoAgument's spline rotation is not rebuilt.       */
+ *   bit 1 vertical, or NULL.  Device pointers, stream-ordered.  AutoAgument's spline rotation: the three calls below. */
 int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* aif_out, float* depth_out, int B, int H, int W,
                              int h, int w, float depth_div, int depth_mode, const float* jitter, const uint8_t* flips,
                              void* stream);
+
+/* AutoAgument's rotation (dff/dataset.py:275-284: scipy.ndimage.rotate(x, degree, reshape=False), i.e. order-3 spline
+ * interpolation, mode 'constant', cval 0, with prefilter) between the flips and the resize, in three stream-ordered steps
+ * on fp32 planes [B,P,H,W] at full resolution (P = 3 RGB planes if bgr, + 1 depth plane if depth, in that order):
+ *   aadff_prepare_planes_u8   decoded arrays -> planes with /255, colour jitter, flips (arguments as above);
+ *   aadff_spline_affine_f32   scipy.ndimage.affine_transform(order=3, mode='constant', cval=0, prefilter=True) per
+ *       plane: xform [B,6] doubles (device) = m00, m01, m10, m11, off0, off1 with input (row, col) = M (output row,
+ *       col) + off -- for a rotation by `degree` M = [[cos, sin], [-sin, cos]], off = centre - M centre, centre =
+ *       ((H-1)/2, (W-1)/2); a sample whose m00 is NaN is copied unchanged.  work holds 2*B*P*H*W floats.  Plane
+ *       clamp_plane (the depth plane; -1 = none) is clamped at 0 afterwards (`depth[depth<0] = 0`);
+ *   aadff_resize_planes_f32   planes -> aif_out [B,3,h,w] / depth_out [B,1,h,w] (either may be NULL; P must match),
+ *       the same resize as aadff_preprocess_rgbd_u8.                                                             */
+int aadff_prepare_planes_u8(const uint8_t* bgr, const uint16_t* depth, float* planes, int B, int H, int W, float depth_div,
+                            const float* jitter, const uint8_t* flips, void* stream);
+int aadff_spline_affine_f32(const float* planes, float* work, float* out, int B, int P, int H, int W, const double* xform,
+                            int clamp_plane, void* stream);
+int aadff_resize_planes_f32(const float* planes, float* aif_out, float* depth_out, int B, int P, int H, int W, int h, int w,
+                            int depth_mode, void* stream);
 
 /* Replaces select_focus_dist(depth, num, mode='linear') (dff/utils.py:4-51), the producer of foc_dist in the
  * training loop: per image the minimum over valid (> 0) depths and the maximum depth, then `num` (> 3) focus

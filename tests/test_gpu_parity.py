@@ -484,6 +484,43 @@ def test_dataset_preparation_matches_reference_datasets(pkg):
     assert stack.shape == (1, 3, 5, 48, 64) and bool(torch.isfinite(stack).all())
 
 
+def test_auto_augment_rotation_on_the_device(pkg):
+    """f4 row, AutoAgument's rotation (dff/dataset.py:275-284: scipy.ndimage.rotate, order-3 spline, 'constant') on the
+    device between the flips and the resize: against what the reference's own Matterport3D(train=True) returned for
+    seeds that draw a rotation (alone / with jitter and both flips / with one flip), against scipy's full-resolution
+    rotation of the decoded arrays, and against the oracle on odd shapes, multiples of 90 degrees and mixed batches."""
+    from oracle import spline_rotate_oracle as so
+    g = load_golden("kat_l_rotate.npz")
+    bgr = T(g["bgr"]).cuda()[None]
+    dep = torch.from_numpy(g["depth"].astype(np.int16)).view(torch.uint16).cuda()[None]
+    for i in range(3):
+        aif, d = pkg.preprocess_rgbd(bgr, dep, (48, 65), depth_div=4000.0, jitter=T(g[f"case{i}_jitter"])[None],
+                                     flips=torch.tensor([int(g[f"case{i}_flips"])], dtype=torch.uint8),
+                                     rotate_deg=[float(g[f"case{i}_degree"])])
+        assert maxabs(aif[0], T(g[f"case{i}_aif"])) < 3e-6 and maxabs(d[0], T(g[f"case{i}_depth"])) < 3e-6, i
+    # no resize: the rotation itself at full resolution
+    H, W = g["bgr"].shape[:2]
+    aif, d = pkg.preprocess_rgbd(bgr, dep, (H, W), depth_div=4000.0, rotate_deg=[float(g["full_degree"])])
+    assert maxabs(aif[0], T(g["full_aif"]).permute(2, 0, 1)) < 3e-6 and maxabs(d[0, 0], T(g["full_depth"])) < 3e-6
+    # a batch: sample 0 not rotated (== the one-launch path), samples 1.. at 90 / 180 / 33 degrees vs the oracle
+    gen = np.random.default_rng(8)
+    for (H, W) in [(37, 50), (16, 16), (5, 23)]:
+        b8 = torch.from_numpy(gen.integers(0, 256, (4, H, W, 3), dtype=np.uint8)).cuda()
+        d16 = torch.from_numpy(gen.integers(0, 8000, (4, H, W)).astype(np.int16)).view(torch.uint16).cuda()
+        degs = [float("nan"), 90.0, 180.0, 33.0]
+        aif, d = pkg.preprocess_rgbd(b8, d16, (H, W), depth_div=1000.0, rotate_deg=degs)
+        plain_a, plain_d = pkg.preprocess_rgbd(b8[:1], d16[:1], (H, W), depth_div=1000.0)
+        assert maxabs(aif[0], plain_a[0]) < 1e-6 and maxabs(d[0], plain_d[0]) < 1e-6
+        for k in (1, 2, 3):
+            oi, od = so.auto_augment_rotate(b8[k].cpu().numpy()[..., ::-1] / 255., d16[k].cpu().view(torch.int16).numpy().astype(np.float64) / 1000, degs[k])
+            assert maxabs(aif[k], torch.from_numpy(oi).float().permute(2, 0, 1)) < 3e-6, (H, W, k)
+            assert maxabs(d[k, 0], torch.from_numpy(od).float()) < 3e-5, (H, W, k)        # depths up to 8 m
+        only_img, none_d = pkg.preprocess_rgbd(b8, None, (H, W), rotate_deg=degs)
+        assert none_d is None and maxabs(only_img, aif) < 1e-6
+        none_a, only_d = pkg.preprocess_rgbd(None, d16, (H, W), depth_div=1000.0, rotate_deg=degs)
+        assert none_a is None and maxabs(only_d, d) < 1e-6
+
+
 # --------------------------------------------------------------------------- oracle on seeded inputs, edge cases
 @pytest.mark.parametrize("N,C,H,W", [(1, 3, 1, 1), (1, 3, 9, 1), (1, 3, 1, 21), (1, 1, 13, 37), (3, 4, 8, 16), (1, 5, 9, 17),
                                      (2, 3, 7, 130)])

@@ -131,3 +131,28 @@ def test_oracle_matches_reference_at_baseline_sizes(rf50mm_weights):
     foc_m = orc.synthetic_focus(dm, 5)
     out = orc.render(*rf50mm_weights, img[3:4], -dm[3:4] * 1e3, -foc_m[3:4, 4] * 1e3, 11)
     assert float((out[0, :, ::2, ::2] - torch.from_numpy(g["out_full_img3"])[:, 4]).abs().max()) < 2e-6
+
+
+def test_spline_rotate_oracle_vs_scipy_and_reference_golden():
+    """AutoAgument's rotation (dff/dataset.py:275-284): the oracle's restatement of scipy's order-3 spline rotation
+    against scipy itself (prefilter: recursion and two-sided-sum form; rotation incl. multiples of 90 degrees, where
+    the in/out-of-image decision sits exactly on the border) and against the full-resolution output stored in
+    kat_l_rotate.npz (scipy.ndimage.rotate on the decoded float64 arrays, as the reference calls it)."""
+    from oracle import spline_rotate_oracle as so
+    ndimage = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(4)
+    for (H, W) in [(9, 13), (40, 56), (5, 70), (2, 3)]:
+        img, dep = rng.random((H, W, 3)), rng.random((H, W)) * 5
+        f = ndimage.spline_filter(dep, 3, output=np.float64, mode="mirror")
+        assert np.abs(f - so.prefilter_axis(so.prefilter_axis(dep, 0), 1)).max() < 1e-12
+        if min(H, W) > 1:
+            assert np.abs(f - so.prefilter_fir(so.prefilter_fir(dep, 0), 1)).max() < 1e-7      # z^17 truncation
+        for deg in (0, 17, 45, 90, 133, 179):
+            ri, rd = ndimage.rotate(img, deg, reshape=False), ndimage.rotate(dep, deg, reshape=False)
+            rd[rd < 0] = 0
+            oi, od = so.auto_augment_rotate(img, dep, deg)
+            assert np.abs(ri - oi).max() < 1e-12 and np.abs(rd - od).max() < 1e-12, (H, W, deg)
+    g = load_golden("kat_l_rotate.npz")
+    a64 = g["bgr"][..., ::-1] / 255.
+    oi, od = so.auto_augment_rotate(a64, g["depth"] / 4000, float(g["full_degree"]))
+    assert np.abs(oi - g["full_aif"]).max() < 1e-6 and np.abs(od - g["full_depth"]).max() < 1e-6
