@@ -1120,7 +1120,7 @@ int aadff_preprocess_rgbd_u8(const uint8_t* bgr, const uint16_t* depth, float* a
     const long long per_image = (long long)h * w;
     const dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 148 * 16), (unsigned)B);
     if (B > 65535) return fail(AADFF_E_INVALID, "batch too large for one launch");
-    preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    preprocess_rgbd_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;
@@ -1179,7 +1179,7 @@ int aadff_resize_planes_f32(const float* planes, float* aif_out, float* depth_ou
     a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.depth_div = 1.f; a.depth_mode = depth_mode;
     const long long per_image = (long long)h * w;
     const dim3 grid((unsigned)std::min<long long>((per_image + 255) / 256, 148 * 16), (unsigned)B);
-    preprocess_rgbd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    preprocess_rgbd_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return AADFF_OK;

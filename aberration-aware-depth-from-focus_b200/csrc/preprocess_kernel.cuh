@@ -53,6 +53,7 @@ constexpr int PP_MAXW = 12;      // filter taps per axis kept in registers (down
 // grid = (chunks of output pixels, image): a block works on ONE image, so the whole per-value arithmetic of the image --
 // /255 and the colour jitter, both evaluated in double like the reference's numpy code and then rounded to fp32 as its
 // astype('float32') does -- is a 256-entry table in shared memory: per tap and channel one byte load, one LDS, one FFMA.
+template <bool FSRC>      // FSRC: read the fp32 planes `fsrc` instead of the decoded uint8 / uint16 arrays
 __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessArgs a) {
     __shared__ float lut[256];
     const int b = blockIdx.y;
@@ -67,10 +68,10 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
     const long long total = (long long)a.h * a.w;
     for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(id % a.w), oy = (int)(id / a.w);
-        const int fl = (a.flips && !a.fsrc) ? a.flips[b] : 0;
+        const int fl = (a.flips && !FSRC) ? a.flips[b] : 0;
         const bool flx = fl & 1, fly = fl & 2;
         const long long fplane = (long long)a.H * a.W;
-        const float* fs = a.fsrc ? a.fsrc + (long long)b * a.fsrc_planes * fplane : nullptr;
+        const float* fs = FSRC ? a.fsrc + (long long)b * a.fsrc_planes * fplane : nullptr;
         int ylo, yn, xlo, xn;
         float yc, yinv, xc, xinv;
         aa_window(oy, a.H, a.h, ylo, yn, yc, yinv);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
                 float racc[3] = {0.f, 0.f, 0.f};
                 auto tap = [&](int jx, float wx) {
                     const int sx = flx ? a.W - 1 - (xlo + jx) : xlo + jx;
-                    if (fs) {
+                    if (FSRC) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) racc[c] = fmaf(wx, frow[c * fplane + sx], racc[c]);
                     } else {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) preprocess_rgbd_kernel(const PreprocessAr
             const uint16_t* dp = a.depth + (long long)b * a.H * a.W;
             const float* fd = fs + (long long)a.fsrc_depth_plane * fplane;
             auto at = [&](int sy, int sx) {
-                if (fs) return fd[(long long)sy * a.W + sx];
+                if (FSRC) return fd[(long long)sy * a.W + sx];
                 sy = fly ? a.H - 1 - sy : sy;
                 sx = flx ? a.W - 1 - sx : sx;
                 return (float)dp[(long long)sy * a.W + sx] / a.depth_div;
