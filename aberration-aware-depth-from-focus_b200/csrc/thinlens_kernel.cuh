@@ -216,6 +216,24 @@ thinlens_render_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMap
 // CTA tile = 8 rows x 64 columns (warp = row, lane j = columns 2j, 2j+1); halo staging (TMA box / clamped cp.async,
 // double-buffered) as above.  ~5 instead of ~9 instructions per tap and pixel.
 constexpr int TL2_TILE_W = 64;
+#ifndef AADFF_TL2_FFMA2
+#define AADFF_TL2_FFMA2 0         // 1: packed fma.rn.f32x2 (FFMA2, sm_100) over the aligned pairs of a window: built, same results, measured
+                                  // not to pay (k = 11: 21.96 against 22.27 Gpix/s; k = 31: 4.14 against 5.11 -- the pair-building MOVs and
+                                  // 148 registers cost more than the halved FFMA count saves), profiles/NOTES_r02.md
+#endif
+__device__ __forceinline__ unsigned long long tl_pack2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void tl_unpack2(unsigned long long v, float& x, float& y) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long tl_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 #ifndef AADFF_TL2_MINB
 #define AADFF_TL2_MINB 1          // resident CTAs per SM the register allocation aims at
 #endif
@@ -349,10 +367,18 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
 #pragma unroll
                 for (int d = 0; d <= R; ++d) g[p][d] = exp2f((float)(d * d) * cexp[p]);
             float acc[2][TL_MAXC], wsum[2] = {0.f, 0.f};
+#if AADFF_TL2_FFMA2
+            unsigned long long acc2[2][TL_MAXC];            // (even-element, odd-element) partial sums
+#endif
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int c = 0; c < TL_MAXC; ++c) acc[p][c] = 0.f;
+                for (int c = 0; c < TL_MAXC; ++c) {
+                    acc[p][c] = 0.f;
+#if AADFF_TL2_FFMA2
+                    acc2[p][c] = 0ull;
+#endif
+                }
             const float* ib = bufs + cur * buf_floats + warp * BW + (SH - WOFF) + 2 * lane;
             // absent channels re-read channel 0 (results discarded at the store): no branches in the tap loop
             const int cs[TL_MAXC] = {0, a.cn > 1 ? CSTRIDE : 0, a.cn > 2 ? 2 * CSTRIDE : 0};
@@ -373,6 +399,17 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                     rs = fmaf(2.f, rs, wt[p][0]);
                     wsum[p] += (da == 0) ? rs : 2.f * rs;
                 }
+#if AADFF_TL2_FFMA2
+                unsigned long long wp[2][NLD];                  // packed weights of the aligned window pairs
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int l = 0; l < NLD; ++l) {
+                        const int j0 = 2 * l - WOFF - p, j1 = j0 + 1;          // taps of window elements 2l, 2l+1
+                        const int d0 = j0 <= R ? R - j0 : j0 - R, d1 = j1 <= R ? R - j1 : j1 - R;
+                        wp[p][l] = (j0 >= 0 && j1 < KS) ? tl_pack2(wt[p][d0], wt[p][d1]) : 0ull;
+                    }
+#endif
 #if AADFF_TL2_UNROLL_SIDE
 #pragma unroll
 #else
@@ -382,6 +419,33 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                     if (side == 1 && da == 0) break;
                     const int i = side ? R + da : R - da;
                     const float* prow = ib + i * BW;
+#if AADFF_TL2_FFMA2
+                    // window element a = WOFF + p + j holds tap j of pixel p.  The aligned pairs (2l, 2l+1) that lie
+                    // inside a pixel's tap range take one FFMA2 against the packed weights (wt[|j-R|], wt[|j+1-R|]);
+                    // the odd element at either end takes a scalar FFMA.
+#pragma unroll
+                    for (int c = 0; c < TL_MAXC; ++c) {
+                        const float2* pw = reinterpret_cast<const float2*>(prow + cs[c]);
+                        float2 win2[NLD];
+#pragma unroll
+                        for (int l = 0; l < NLD; ++l) win2[l] = pw[l];
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const int a_lo = WOFF + p, a_hi = a_lo + KS - 1;
+#pragma unroll
+                            for (int l = 0; l < NLD; ++l) {
+                                const int a0 = 2 * l, a1 = 2 * l + 1;
+                                if (a0 >= a_lo && a1 <= a_hi) {
+                                    acc2[p][c] = tl_ffma2(tl_pack2(win2[l].x, win2[l].y), wp[p][l], acc2[p][c]);
+                                } else if (a1 == a_lo) {                       // leading single: tap 0
+                                    acc[p][c] = fmaf(win2[l].y, wt[p][R], acc[p][c]);
+                                } else if (a0 == a_hi) {                       // trailing single: tap KS-1
+                                    acc[p][c] = fmaf(win2[l].x, wt[p][R], acc[p][c]);
+                                }
+                            }
+                        }
+                    }
+#else
 #pragma unroll
                     for (int c = 0; c < TL_MAXC; ++c) {
                         const float2* pw = reinterpret_cast<const float2*>(prow + cs[c]);
@@ -398,6 +462,7 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                             for (int j = 0; j < KS; ++j)
                                 acc[p][c] = fmaf(win[WOFF + p + j], wt[p][j <= R ? R - j : j - R], acc[p][c]);
                     }
+#endif
                 }
             }
 #pragma unroll
@@ -405,8 +470,14 @@ thinlens_render2_kernel(const ThinLensArgs a, const __grid_constant__ CUtensorMa
                 if (!ok[p]) continue;
                 const float inv = __fdiv_rn(1.0f, wsum[p]);     // the centre tap always passes the mask: wsum >= 1
 #pragma unroll
-                for (int c = 0; c < TL_MAXC; ++c)
+                for (int c = 0; c < TL_MAXC; ++c) {
+#if AADFF_TL2_FFMA2
+                    float ex, ey;
+                    tl_unpack2(acc2[p][c], ex, ey);
+                    acc[p][c] += ex + ey;
+#endif
                     if (c < a.cn) a.out[((long long)(n * a.C + a.c0 + c) * a.H + h) * a.W + w + p] = acc[p][c] * inv;
+                }
             }
         }
         __syncthreads();
