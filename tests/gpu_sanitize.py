@@ -67,3 +67,21 @@ print("fast two tiles", float(lens.render_stack(img, dep, foc, mode="fast").mean
 aadff_b200.native.lib.aadff_debug_set_flags(8)
 print("cluster multicast", float(lens.render_stack(img, dep, foc, mode="parity").mean()))
 aadff_b200.native.lib.aadff_debug_set_flags(0)
+# ---- round 2, second half: strip-walking gather (every plan; W % 4 == 0, partial strips, runs crossing strips and
+# images), two-pixel thin-lens kernel on odd widths, AutoAgument's spline rotation
+for ks, (n_, h_, w_) in ((11, (2, 19, 68)), (7, (3, 9, 332)), (3, (1, 5, 4)), (13, (1, 33, 132)), (15, (1, 20, 64))):
+    im = torch.rand(n_, 3, h_, w_, device="cuda")
+    pf = torch.rand(n_, h_, w_, ks, ks, device="cuda")
+    for flags in (0, 8192, 1024, 4096):
+        aadff_b200.native.lib.aadff_debug_set_flags(flags)
+        v = float(aadff_b200.local_psf_render(im, pf, ks).mean())
+        aadff_b200.native.lib.aadff_debug_set_flags(0)
+    print("strip gather ks", ks, (n_, h_, w_), v)
+tl4 = aadff_b200.ThinLens(50.0, 1.8, 7, [36.0, 24.0], (33, 67)).to("cuda")
+print("thinlens two-pixel odd W", float(tl4.render(torch.rand(1, 5, 33, 67, device="cuda"), 300 + 6000 * torch.rand(1, 1, 33, 67, device="cuda"),
+                                                   torch.tensor([1500.0], device="cuda")).mean()))
+a, d = aadff_b200.preprocess_rgbd(bgr, d16, (40, 56), jitter=torch.tensor([[0.5, 0.1], [-1.0, 0.0]]), flips=torch.tensor([3, 0], dtype=torch.uint8),
+                                  rotate_deg=[33.0, None])
+print("preprocess + rotation", float(a.mean()), float(d.mean()))
+a, d = aadff_b200.preprocess_rgbd(bgr[:, :5, :23].contiguous(), d16[:, :5, :23].contiguous(), (5, 23), rotate_deg=[90.0, 171.0])
+print("rotation of a 5 x 23 image", float(a.mean()), float(d.mean()))
