@@ -686,7 +686,8 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.trace = g_trace.load();
     P.dbg = (uint32_t)g_dbg_flags.load();
     // shared-memory carve-up
-    const uint32_t halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 16;   // float4 per pixel
+    uint32_t halo_bytes = (uint32_t)(TC_TILE_H + ra.ks - 1) * TC_HALO_PITCH * 16;          // float4 per pixel
+    if (probes != nullptr) halo_bytes = std::max<uint32_t>(halo_bytes, 8 * 32 * 9 * 4);        // pred mode: the store staging lives there
     const uint32_t bias_bytes = (uint32_t)(h->n_bias - h->head_bias0) * 4;                 // head bias only
     const uint32_t ones_bytes = 2 * TC_A_LBO;                                              // constant A operand of the bias slabs
     const uint32_t bslab_bytes = 2 * TC_BSLAB_BYTES;                                        // bias-slab slot + its block of zeros

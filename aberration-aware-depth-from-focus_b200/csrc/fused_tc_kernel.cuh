@@ -529,6 +529,8 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
         TcTrace<TRACE> tr; tr.init((lane == 0 && (e == 0 || e == 7)) ? P.trace : nullptr, e == 0 ? 2 : 3);
         const float NEG_LOG2E = -1.4426950408889634f;
         const bool fine = kslab_c == 1;         // 16-column first hand-offs (3-term modes)
+        // pred mode: one head block of <= 128 columns -> its values fit in registers until the row sum is known
+        const bool pred_one_block = PRED && (P.n_groups - P.n_hidden == 1) && (P.g[P.n_hidden].N <= 128);
 
         // tile -> (image n, slice s, tile origin); depth / focus of this thread's pixel are fetched
         // one tile ahead so that layer 0 (the head of the serial chain) never waits on HBM
@@ -708,6 +710,68 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 }
                 const int gN = P.g[gi].N, gtap0 = P.g[gi].tap0;
                 const float* bias = s_bias + (P.g[gi].bias_off - P.bias_skip);
+                if constexpr (PRED) {
+                    if (pred_one_block) {
+                        // ---- pred with a single head block of <= 128 columns (ks <= 11): the thread's <= 64 sigmoid values stay in
+                        // registers until the row sum is known, then go out NORMALISED and COALESCED.  (Storing each
+                        // thread's own row directly makes every store instruction touch 32 rows = 32 sectors, and
+                        // the rescale pass re-reads and re-writes them the same way: the stores, not the MMAs, set
+                        // the pace -- 184 Mprobes/s against 440 Mpix*slices/s for the render.)  Eight columns at a
+                        // time are transposed through the (unused in pred mode) halo area: [32 rows][8 + 1] floats
+                        // per warp, then lane = (row % 4, column) writes 4 rows x 32 B per instruction.
+                        float keep[2][32];
+#pragma unroll
+                        for (int ci = 0; ci < 2; ++ci) {
+                            const int c32 = hh * 32 + ci * 64;
+                            if (c32 < gN) {
+                                uint32_t rr[32];
+                                tmem_ld32(t_lane + buf * 256 + c32, rr);
+                                const int nvalid = kk - (gtap0 + c32);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int u = 0; u < 32; ++u) {
+                                    float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
+                                    sg = (u < nvalid) ? sg : 0.f;
+                                    keep[ci][u] = sg;
+                                    ssum += sg;
+                                }
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 32; ++u) keep[ci][u] = 0.f;
+                            }
+                        }
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_accfree(buf));
+                        ++gcount;
+                        s_red[row * 5 + hh] = ssum;
+                        named_bar_sync(2 + q, 64);
+                        const float inv = 1.0f / fmaxf(s_red[row * 5] + s_red[row * 5 + 1], 1e-12f);
+                        float* stg = reinterpret_cast<float*>(s_halo) + e * (32 * 9);
+                        const long long row0 = tile * TC_M + q * 32;            // first probe of this warp's 32 rows
+                        const int rsub = lane >> 3, csub = lane & 7;
+#pragma unroll
+                        for (int ci = 0; ci < 2; ++ci) {
+#pragma unroll
+                            for (int pc = 0; pc < 4; ++pc) {
+                                const int c0 = gtap0 + hh * 32 + ci * 64 + pc * 8;
+                                if (c0 >= kk) continue;                          // warp-uniform
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) stg[lane * 9 + j] = keep[ci][pc * 8 + j] * inv;
+                                __syncwarp();
+#pragma unroll
+                                for (int rb = 0; rb < 8; ++rb) {
+                                    const int rloc = rb * 4 + rsub;
+                                    const float v = stg[rloc * 9 + csub];
+                                    if (row0 + rloc < P.n_probes && c0 + csub < kk)
+                                        P.psf_out[(row0 + rloc) * kk + c0 + csub] = v;
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        continue;
+                    }
+                }
 #pragma unroll 1
                 for (int c32 = hh * 32; c32 < gN; c32 += 64) {
                     uint32_t rr[32];
@@ -765,6 +829,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 ++gcount;
             }
             if constexpr (PRED) {
+                if (pred_one_block) continue;                          // normalised and stored above
                 // ---- exchange the partial sums of the two column halves, then rescale what this thread wrote
                 s_red[row * 5 + hh] = ssum;
                 named_bar_sync(2 + q, 64);
