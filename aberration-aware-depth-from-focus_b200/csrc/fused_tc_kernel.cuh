@@ -782,15 +782,34 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                     const int nvalid = kk - tap_first;     // >= 32 for every group but the padded last one
                     tmem_ld_wait();
                     if constexpr (PRED) {
-                        // un-normalised sigmoid values go straight to the output; they are rescaled below
-                        float* orow = P.psf_out + m_row * kk + tap_first;
+                        // several head blocks (ks >= 13): the un-normalised sigmoid values go out now -- transposed
+                        // through the halo area like above, so that a store instruction covers 4 rows x 32 B instead
+                        // of 32 rows -- and are rescaled below
+                        float sgv[32];
 #pragma unroll
                         for (int u = 0; u < 32; ++u) {
-                            if (u < nvalid) {
-                                const float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
-                                ssum += sg;
-                                if (valid) orow[u] = sg;
+                            float sg = rcp_approx(1.0f + ex2_approx(fmaf(__uint_as_float(rr[u]), NEG_LOG2E, bias[c32 + u])));
+                            sg = (u < nvalid) ? sg : 0.f;
+                            sgv[u] = sg;
+                            ssum += sg;
+                        }
+                        float* stg = reinterpret_cast<float*>(s_halo) + e * (32 * 9);
+                        const long long row0 = tile * TC_M + q * 32;
+                        const int rsub = lane >> 3, csub = lane & 7;
+#pragma unroll
+                        for (int pc = 0; pc < 4; ++pc) {
+                            const int c0 = tap_first + pc * 8;
+                            if (c0 >= kk) continue;                              // warp-uniform
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) stg[lane * 9 + j] = sgv[pc * 8 + j];
+                            __syncwarp();
+#pragma unroll
+                            for (int rb = 0; rb < 8; ++rb) {
+                                const int rloc = rb * 4 + rsub;
+                                const float v = stg[rloc * 9 + csub];
+                                if (row0 + rloc < P.n_probes && c0 + csub < kk) P.psf_out[(row0 + rloc) * kk + c0 + csub] = v;
                             }
+                            __syncwarp();
                         }
                     } else if (nvalid >= 32) {
                         // branch-free so that the MUFU / LDS latencies of different taps overlap
@@ -833,15 +852,14 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
                 // ---- exchange the partial sums of the two column halves, then rescale what this thread wrote
                 s_red[row * 5 + hh] = ssum;
                 named_bar_sync(2 + q, 64);
-                const float inv = 1.0f / fmaxf(s_red[row * 5] + s_red[row * 5 + 1], 1e-12f);
-                if (valid) {
-                    for (int gi = P.n_hidden; gi < P.n_groups; ++gi) {
-                        for (int c32 = hh * 32; c32 < P.g[gi].N; c32 += 64) {
-                            const int t0 = P.g[gi].tap0 + c32;
-                            float* orow = P.psf_out + m_row * kk + t0;
-                            for (int u = 0; u < 32 && t0 + u < kk; ++u) orow[u] *= inv;
-                        }
-                    }
+                // (the barrier also orders the two warps' global stores of this quadrant's rows before the re-read)
+                // each of the two warps rescales sixteen of the quadrant's rows, lanes along the taps: coalesced
+                for (int rloc = hh * 16; rloc < hh * 16 + 16; ++rloc) {
+                    const long long grow = tile * TC_M + q * 32 + rloc;
+                    if (grow >= P.n_probes) break;
+                    const float inv = 1.0f / fmaxf(s_red[(q * 32 + rloc) * 5] + s_red[(q * 32 + rloc) * 5 + 1], 1e-12f);
+                    float* orow = P.psf_out + grow * kk;
+                    for (int t = lane; t < kk; t += 32) orow[t] *= inv;
                 }
                 continue;
             }
