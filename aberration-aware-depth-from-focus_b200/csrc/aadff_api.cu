@@ -316,13 +316,18 @@ struct aadff_trainer {
     size_t n_params = 0;
     float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
     std::vector<float*> act;                   // act[l] = input of layer l, [batch, dims[l]]
-    float *z = nullptr, *p = nullptr, *target = nullptr, *dz[2] = {nullptr, nullptr}, *loss = nullptr;
+    float *z = nullptr, *p = nullptr, *target = nullptr, *loss = nullptr;
+    std::vector<float*> dz;                    // dz[l] = dL/d(pre-activation of layer l), [batch, dims[l+1]]: one buffer per
+                                               // layer, because dW_l (side branch of the graph) reads dz[l] while the main
+                                               // branch already produces dz[l-1], dz[l-2], ...
     AdamHyper* hyper = nullptr;
     AdamHyper host_hyper{};
     long long step = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};  // capture-time fork targets (created before the capture begins)
+    std::vector<cudaEvent_t> evs;
 };
 
 static void trainer_free(aadff_trainer* t) {
@@ -331,9 +336,12 @@ static void trainer_free(aadff_trainer* t) {
     if (t->exec) cudaGraphExecDestroy(t->exec);
     if (t->graph) cudaGraphDestroy(t->graph);
     if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    for (cudaEvent_t ev : t->evs) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) if (t->side[i]) cudaStreamDestroy(t->side[i]);
     for (float* a : t->act) cudaFree(a);
     cudaFree(t->params); cudaFree(t->grads); cudaFree(t->m); cudaFree(t->v);
-    cudaFree(t->z); cudaFree(t->p); cudaFree(t->target); cudaFree(t->dz[0]); cudaFree(t->dz[1]);
+    cudaFree(t->z); cudaFree(t->p); cudaFree(t->target);
+    for (float* d : t->dz) cudaFree(d);
     cudaFree(t->loss); cudaFree(t->hyper);
     delete t;
 }
@@ -345,9 +353,15 @@ static void tg_launch(cudaStream_t st, const float* A, long long sa_i, long long
     train_gemm_kernel<EPI><<<grid, TG_NT, 0, st>>>(A, sa_i, sa_k, B, sb_k, sb_j, C, M, N, K, aux);
 }
 
-// the whole step (forward, loss, backward, AdamW) as a stream of launches: recorded once into a CUDA graph
+// the whole step (forward, loss, backward, AdamW): recorded once into a CUDA graph.  Only the dX chain of the backward
+// pass is serial; the weight gradients dW_l = dZ_l^T X_l and the bias gradients (column sums of dZ_l) hang off it, so they
+// are recorded on two side streams (forked / joined with events: parallel branches of the graph) -- the critical path
+// shrinks from 3 L + ... to L launches of the backward pass.
 static int trainer_record(aadff_trainer* t, cudaStream_t st) {
     const int L = t->n_layers, M = t->batch;
+    cudaStream_t* side = t->side;
+    size_t next_ev = 0;
+    auto new_event = [&]() { return t->evs[next_ev++]; };      // L + 2 events, created before the capture began
     for (int l = 0; l < L; ++l) {
         const int K = t->dims[l], N = t->dims[l + 1];
         const float* W = t->params + t->w_off[l];
@@ -355,22 +369,28 @@ static int trainer_record(aadff_trainer* t, cudaStream_t st) {
         if (l < L - 1) tg_launch<TG_BIAS_RELU>(st, t->act[l], K, 1, W, 1, K, t->act[l + 1], M, N, K, b);
         else tg_launch<TG_BIAS>(st, t->act[l], K, 1, W, 1, K, t->z, M, N, K, b);
     }
-    train_head_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(t->z, t->target, t->p, t->dz[0], t->loss, M, t->kk);
-    int cur = 0;
+    train_head_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(t->z, t->target, t->p, t->dz[L - 1], t->loss, M, t->kk);
     for (int l = L - 1; l >= 0; --l) {
         const int K = t->dims[l], N = t->dims[l + 1];
         const float* W = t->params + t->w_off[l];
-        const float* dZ = t->dz[cur];
-        tg_launch<TG_PLAIN>(st, dZ, 1, N, t->act[l], K, 1, t->grads + t->w_off[l], N, K, M, nullptr);      // dW = dZ^T X
-        train_colsum_kernel<<<(N + 255) / 256, 256, 0, st>>>(dZ, t->grads + t->b_off[l], M, N);
-        if (l > 0) {
-            tg_launch<TG_RELU_MASK>(st, dZ, N, 1, W, K, 1, t->dz[cur ^ 1], M, K, N, t->act[l]);            // dX = dZ W, masked
-            cur ^= 1;
-        }
+        const float* dZ = t->dz[l];
+        cudaEvent_t ready = new_event();                                                                    // dZ_l exists
+        cudaEventRecord(ready, st);
+        cudaStreamWaitEvent(side[0], ready, 0);
+        cudaStreamWaitEvent(side[1], ready, 0);
+        tg_launch<TG_PLAIN>(side[0], dZ, 1, N, t->act[l], K, 1, t->grads + t->w_off[l], N, K, M, nullptr);  // dW = dZ^T X
+        train_colsum_kernel<<<(N + 255) / 256, 256, 0, side[1]>>>(dZ, t->grads + t->b_off[l], M, N);
+        if (l > 0) tg_launch<TG_RELU_MASK>(st, dZ, N, 1, W, K, 1, t->dz[l - 1], M, K, N, t->act[l]);        // dX = dZ W, masked
+    }
+    for (int i = 0; i < 2; ++i) {                                                                           // join
+        cudaEvent_t done = new_event();
+        cudaEventRecord(done, side[i]);
+        cudaStreamWaitEvent(st, done, 0);
     }
     train_adamw_kernel<<<(int)std::min<size_t>((t->n_params + 255) / 256, 1184), 256, 0, st>>>(
         t->params, t->grads, t->m, t->v, (long long)t->n_params, t->hyper);
-    CUDA_TRY(cudaGetLastError());
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AADFF_E_CUDA, std::string("trainer_record: ") + cudaGetErrorString(e));
     return AADFF_OK;
 }
 
@@ -1238,10 +1258,21 @@ int aadff_trainer_create(const float* const* weights, const float* const* biases
     }
     TR_TRY(dalloc(&t->z, (size_t)batch * t->kk)); TR_TRY(dalloc(&t->p, (size_t)batch * t->kk));
     TR_TRY(dalloc(&t->target, (size_t)batch * t->kk));
-    TR_TRY(dalloc(&t->dz[0], (size_t)batch * wmax)); TR_TRY(dalloc(&t->dz[1], (size_t)batch * wmax));
+    for (int l = 0; l < n_layers; ++l) {
+        float* d = nullptr;
+        TR_TRY(dalloc(&d, (size_t)batch * dims[l + 1]));
+        t->dz.push_back(d);
+    }
+    (void)wmax;
     TR_TRY(dalloc(&t->loss, 1));
     TR_TRY(cudaMalloc(reinterpret_cast<void**>(&t->hyper), sizeof(AdamHyper)));
     TR_TRY(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) TR_TRY(cudaStreamCreateWithFlags(&t->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < n_layers + 2; ++i) {
+        cudaEvent_t ev = nullptr;
+        TR_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        t->evs.push_back(ev);
+    }
     TR_TRY(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
     const int rc = trainer_record(t, t->cap_stream);
     cudaError_t ce = cudaStreamEndCapture(t->cap_stream, &t->graph);
