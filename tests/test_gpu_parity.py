@@ -424,7 +424,7 @@ def test_train_psfnet_matches_torch_autograd(pkg):
         nat.check(nat.lib.aadff_trainer_step(trainer.handle, inp_d.data_ptr(), tgt_d.data_ptr(), lr_i,
                                              loss_dev.data_ptr(), None))
         torch.cuda.synchronize()
-        assert abs(float(loss_dev) - float(loss)) < 1e-6 * max(1.0, float(loss)) + 1e-9, it
+        assert abs(float(loss_dev) - float(loss.detach())) < 1e-6 * max(1.0, float(loss.detach())) + 1e-9, it
         if it == 0:
             gw, gb = trainer.read(1)
             for lin, a, b in zip([m for m in net if isinstance(m, nn.Linear)], gw, gb):
@@ -941,7 +941,8 @@ def test_reference_training_script_runs_unchanged_on_the_shadow_package(tmp_path
     shutil.copy(os.path.join(ref, "2_aber_aware_dff_aif.py"), work / "2_aber_aware_dff_aif.py")
     shutil.copy(os.path.join(ref, "lenses/rf50mm/lens.json"), work / "lenses/rf50mm/lens.json")
     shutil.copy(os.path.join(ref, "ckpt/rf50mm/PSFNet480x640_ks11.pkl"), work / "ckpt/rf50mm/PSFNet480x640_ks11.pkl")
-    yml = open(os.path.join(ref, "configs/aber_aware_dff_aif.yml")).read()
+    with open(os.path.join(ref, "configs/aber_aware_dff_aif.yml")) as fh:
+        yml = fh.read()
     yml = yml.replace("dffnet_pretrained: './ckpt/rf50mm/aifnet_stack8_480x640.pkl'", "dffnet_pretrained: ''").replace("epochs: 20", "epochs: 1")
     assert "dffnet_pretrained: ''" in yml and "epochs: 1 " in yml
     (work / "configs/aber_aware_dff_aif.yml").write_text(yml)
