@@ -678,12 +678,16 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     P.n_bias = h->n_bias;
     P.bias_skip = h->head_bias0;                               // hidden biases live in the bias slabs
     P.kk = h->kk;
+    // debug flags bits 16..19: first two-term group of AADFF_MODE_ECON for this launch (0 = the shipped pattern, L5 =
+    // group 4; later groups trade speed for accuracy -- tests/gpu_econ_certificate.py sweeps it; runs the generic kernel)
+    const int econ_first_dbg = (g_dbg_flags.load() >> 16) & 15;
+    const int econ_first = (econ_first_dbg > TC_ECON_FIRST_GROUP) ? econ_first_dbg : TC_ECON_FIRST_GROUP;
     for (int i = 0; i < h->n_groups; ++i) {
         P.g[i] = h->groups[i];
         const bool hidden = i < h->n_hidden;
         P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1
                        : (mode == AADFF_MODE_MIXED && i >= TC_MIXED_FIRST_GROUP) ? 1
-                       : (mode == AADFF_MODE_ECON && i >= TC_ECON_FIRST_GROUP) ? 2   // L5.. and the head: fp16 weights
+                       : (mode == AADFF_MODE_ECON && i >= econ_first) ? 2              // L5.. and the head: fp16 weights
                        : 3;
         if (mode == AADFF_MODE_ECON && P.g[i].terms == 2 && !(g_dbg_flags.load() & 256))
             P.g[i].w_off = h->w_off_econ[i];                   // calibrated rounding (debug flag 256: plain rounding)

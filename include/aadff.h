@@ -195,7 +195,8 @@ int aadff_debug_trace_entries(void);
  * weights instead of the calibrated ones, 512 = aadff_local_psf_render_f32 through the register-streaming kernel
  * also where the strip-walking kernel would run (ks <= 15, W % 4 == 0); 8192 / 1024 / 4096 = the strip-walking
  * kernel with its shared-memory plan 0 / 1 / 2 forced (default: the widest strips that divide W well),
- * 2048 = aadff_thinlens_render_f32 through the one-pixel-per-thread kernel.                      */
+ * 2048 = aadff_thinlens_render_f32 through the one-pixel-per-thread kernel.  Bits 16..19 (value g > 4): AADFF_MODE_ECON
+ * starts its two-term evaluation at layer group g instead of 4 (L5) -- accuracy / speed sweep, generic kernel.      */
 int aadff_debug_set_flags(int flags);
 /* Host-only: the output-error-calibrated fp16 rounding used by AADFF_MODE_ECON (csrc/econ_calib.h) for one layer.
  * W [N][K], A [NC][K] = sample input activations of the layer, out [N][K] = fp16-representable values.  No GPU. */
