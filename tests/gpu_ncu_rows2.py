@@ -1,3 +1,5 @@
+"""Workload for the ncu capture of the final secondary kernels (profiles/r02b_ncu_rows_final.md): thin lens, strip
+gather k = 11 / 7, fp32 mode, tensor-core pred.   ncu --set full -k regex:... --launch-skip 5 -c 5 python tests/gpu_ncu_rows2.py"""
 import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import aadff_b200

@@ -1,3 +1,5 @@
+"""Timing of preprocess_rgbd with and without AutoAgument's spline rotation against scipy.ndimage.rotate on the host
+(profiles/r02b_rotate_time.txt)."""
 import os, sys, time, torch, numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import aadff_b200
