@@ -126,7 +126,7 @@ class PSFNet(nn.Module):
     @torch.no_grad()
     def pred(self, inp, mode=None):
         """inp [...,4] = (x, y, z, foc_z) -> psf [..., ks, ks].  mode=None: fp32 CUDA-core kernel (operation for
-        operation with the reference); 'parity' / 'econ' / 'mixed' / 'fast': the tensor-core kernel (~30x faster)."""
+        operation with the reference); 'parity' / 'econ8' / 'econ' / 'mixed' / 'fast': the tensor-core kernel (~30x faster)."""
         psf = PSFNet._mlp_eval(self, inp, "fp32" if mode is None else mode)
         return psf.reshape(*psf.shape[:-1], self.kernel_size, self.kernel_size)
 

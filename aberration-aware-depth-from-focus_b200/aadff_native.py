@@ -17,8 +17,9 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("AADFF_LIB_PATH") or os.path.join(_HERE, "libaadff.so")   # override: experiments only
 HEADER = os.path.join(_REPO, "include", "aadff.h")
 
-MODE_PARITY, MODE_FAST, MODE_FP32, MODE_MIXED, MODE_ECON = 0, 1, 2, 3, 4
-MODES = {"parity": MODE_PARITY, "fast": MODE_FAST, "fp32": MODE_FP32, "mixed": MODE_MIXED, "econ": MODE_ECON}
+MODE_PARITY, MODE_FAST, MODE_FP32, MODE_MIXED, MODE_ECON, MODE_ECON8 = 0, 1, 2, 3, 4, 5
+MODES = {"parity": MODE_PARITY, "fast": MODE_FAST, "fp32": MODE_FP32, "mixed": MODE_MIXED, "econ": MODE_ECON,
+         "econ8": MODE_ECON8}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -550,6 +550,8 @@ int aadff_psfnet_create(const float* const* weights, const float* const* biases,
         CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, U>, attr, so));
         AADFF_SET_ATTR(0) AADFF_SET_ATTR(1) AADFF_SET_ATTR(3) AADFF_SET_ATTR(13) AADFF_SET_ATTR(12) AADFF_SET_ATTR(15)
 #undef AADFF_SET_ATTR
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, false, 14>, attr, so));      // econ8: no cluster variant
+        CREATE_TRY(cudaFuncSetAttribute(fused_psfnet_render_kernel<false, true, 14>, attr, so));
     }
 #undef CREATE_TRY
     *out = h;
@@ -660,7 +662,8 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
                      long long tile_row1 = -1, const float* probes = nullptr, float* psf_out = nullptr,
                      long long n_probes = 0) {
     if (!h->tc_ok) return fail(AADFF_E_UNSUPPORTED, "tensor-core path unavailable: " + h->tc_why + " (use AADFF_MODE_FP32)");
-    if (mode == AADFF_MODE_ECON) {
+    const bool econ_like = (mode == AADFF_MODE_ECON || mode == AADFF_MODE_ECON8);
+    if (econ_like) {
         const int rc = ensure_econ(h);
         if (rc) return rc;
     }
@@ -670,7 +673,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     }
     TcParams P{};
     P.ra = ra;
-    P.wpack = (mode == AADFF_MODE_ECON) ? h->d_wpack_econ : h->d_wpack;
+    P.wpack = econ_like ? h->d_wpack_econ : h->d_wpack;
     P.bias = h->d_bias_tc;
     P.w0b0 = h->d_w0b0;
     P.n_groups = h->n_groups;
@@ -688,8 +691,9 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
         P.g[i].terms = (mode == AADFF_MODE_FAST) ? 1
                        : (mode == AADFF_MODE_MIXED && i >= TC_MIXED_FIRST_GROUP) ? 1
                        : (mode == AADFF_MODE_ECON && i >= econ_first) ? 2              // L5.. and the head: fp16 weights
+                       : (mode == AADFF_MODE_ECON8 && i >= TC_ECON8_FIRST_GROUP) ? 2   // L8, L9 and the head
                        : 3;
-        if (mode == AADFF_MODE_ECON && P.g[i].terms == 2 && !(g_dbg_flags.load() & 256))
+        if (econ_like && P.g[i].terms == 2 && !(g_dbg_flags.load() & 256))
             P.g[i].w_off = h->w_off_econ[i];                   // calibrated rounding (debug flag 256: plain rounding)
         (void)hidden;
     }
@@ -739,12 +743,13 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     // kernel specialisation (fused_tc_kernel.cuh, template UNI): pattern 3 = all groups three-term (parity), 1 = all
     // single-term with the long ring (fast), 2 = econ, 5 = mixed, 0 = per-group terms at run time; +10 when the ring has
     // four stages and every group consumes a multiple of four of them (ring position of a K-step = compile-time)
-    bool all3 = true, all1 = true, econ_pat = true, mixed_pat = true, aligned = (P.n_stages == 4 && P.kslab == 1);
+    bool all3 = true, all1 = true, econ_pat = true, econ8_pat = true, mixed_pat = true, aligned = (P.n_stages == 4 && P.kslab == 1);
     for (int i = 0; i < h->n_groups; ++i) {
         const int t = P.g[i].terms;
         all3 &= (t == 3);
         all1 &= (t == 1);
         econ_pat &= (t == (i < TC_ECON_FIRST_GROUP ? 3 : 2));
+        econ8_pat &= (t == (i < TC_ECON8_FIRST_GROUP ? 3 : 2));
         mixed_pat &= (t == (i < TC_MIXED_FIRST_GROUP ? 3 : 1));
         aligned &= (((P.g[i].K / TC_SLAB_K) * (t == 3 ? 2 : 1)) % 4 == 0);
     }
@@ -753,10 +758,11 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
     if (all3 && P.kslab == 1) uni = aligned ? 13 : 3;
     else if (all1 && P.kslab == 2) uni = 1;
     else if (econ_pat && aligned) uni = 12;
+    else if (econ8_pat && aligned && h->n_groups > TC_ECON8_FIRST_GROUP) uni = 14;
     else if (mixed_pat && aligned) uni = 15;
     // 2-CTA clusters sharing the weight stream by multicast (fused_tc_kernel.cuh, CL2).  Built, bit-exact, and measured
     // NOT to pay (profiles/NOTES_r02.md: -7 % at c2, +-1 % where power-capped), so it is off unless debug flag 8 asks for it.
-    const bool cl2 = P.probes == nullptr && P.trace == nullptr && uni != 0 && (P.dbg & 8u) && h->num_sms >= 2;
+    const bool cl2 = P.probes == nullptr && P.trace == nullptr && uni != 0 && uni != 14 && (P.dbg & 8u) && h->num_sms >= 2;
     if (cl2) {
         grid = (int)std::min<long long>((P.n_tiles + 1) & ~1ll, (long long)(h->num_sms & ~1));
         cudaLaunchConfig_t cfg{};
@@ -787,7 +793,7 @@ static int launch_tc(aadff_psfnet_t h, RenderArgs ra, int mode, cudaStream_t st,
             else fused_psfnet_render_kernel<false, false, U><<<grid, TC_NT, smem, st>>>(P);               \
             break;
         switch (uni) {
-            AADFF_LAUNCH(1) AADFF_LAUNCH(3) AADFF_LAUNCH(13) AADFF_LAUNCH(12) AADFF_LAUNCH(15)
+            AADFF_LAUNCH(1) AADFF_LAUNCH(3) AADFF_LAUNCH(13) AADFF_LAUNCH(12) AADFF_LAUNCH(14) AADFF_LAUNCH(15)
             default:
                 if (P.probes != nullptr) fused_psfnet_render_kernel<false, true, 0><<<grid, TC_NT, smem, st>>>(P);
                 else fused_psfnet_render_kernel<false, false, 0><<<grid, TC_NT, smem, st>>>(P);
@@ -827,7 +833,7 @@ static int render_stack_impl(aadff_psfnet_t h, const float* img, const float* de
                              float d_max, int mode, void* stream, long long tile_row0, long long tile_row1) {
     if (!h || !img || !depth || !foc || !out || !out_strides) return fail(AADFF_E_INVALID, "null argument");
     if (N < 0 || C < 1 || S < 1 || H < 1 || W < 1) return fail(AADFF_E_INVALID, "bad shape");
-    if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
+    if (mode < 0 || mode > 5) return fail(AADFF_E_INVALID, "unknown mode");
     if (d_max == d_min) return fail(AADFF_E_INVALID, "d_max == d_min");
     if (N == 0) return AADFF_OK;
     DeviceGuard guard(h->device);
@@ -941,7 +947,7 @@ int aadff_psfnet_pred_tc_f32(aadff_psfnet_t h, const float* inp, float* psf, int
     if (!h || !inp || !psf) return fail(AADFF_E_INVALID, "null argument");
     if (M < 0) return fail(AADFF_E_INVALID, "negative M");
     if (mode == AADFF_MODE_FP32) return aadff_psfnet_pred_f32(h, inp, psf, M, stream);
-    if (mode < 0 || mode > 4) return fail(AADFF_E_INVALID, "unknown mode");
+    if (mode < 0 || mode > 5) return fail(AADFF_E_INVALID, "unknown mode");
     if (reinterpret_cast<uintptr_t>(inp) % 16) return fail(AADFF_E_INVALID, "inp must be 16-byte aligned");
     if (M == 0) return AADFF_OK;
     DeviceGuard guard(h->device);

@@ -59,6 +59,8 @@ constexpr int TC_BSLAB_BYTES = TC_HID * 16;   // K-group 0 of a bias slab (the o
 constexpr int TC_TRACE_N = 4096;         // trace entries per role
 constexpr int TC_MIXED_FIRST_GROUP = 3;  // mixed: groups 0..2 (L1..L3) three terms, one term after
 constexpr int TC_ECON_FIRST_GROUP = 4;   // econ: groups 0..3 (L1..L4) three terms, L5.. and the head two (econ_calib.h)
+constexpr int TC_ECON8_FIRST_GROUP = 7;  // econ8: groups 0..6 (L1..L7) three terms, L8, L9 and the head two -- the earliest
+                                         // start whose adversarial worst case stays under 1e-4
 
 struct TcGroup {            // one accumulation group: one layer, or one <=256-column block of the head
     uint32_t w_off;         // byte offset of its first slab in the packed weights
@@ -212,9 +214,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_psfnet_render_kernel(const __g
     const long long first_tile = CL2 ? (long long)(blockIdx.x & ~1u) : (long long)blockIdx.x;
     const long long my_iters = (P.n_tiles > first_tile) ? (P.n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
     constexpr bool ALIGNED = UNI >= 10;
-    const int kslab_c = (UM == 3 || UM == 2 || UM == 5) ? 1 : UM == 1 ? 2 : P.kslab;
+    const int kslab_c = (UM == 3 || UM == 2 || UM == 4 || UM == 5) ? 1 : UM == 1 ? 2 : P.kslab;
     auto terms_of = [&](int gi) -> int {
         return UM == 3 ? 3 : UM == 1 ? 1 : UM == 2 ? (gi < TC_ECON_FIRST_GROUP ? 3 : 2)
+                                         : UM == 4 ? (gi < TC_ECON8_FIRST_GROUP ? 3 : 2)
                                          : UM == 5 ? (gi < TC_MIXED_FIRST_GROUP ? 3 : 1) : (int)P.g[gi].terms;
     };
     extern __shared__ __align__(1024) uint8_t smem[];

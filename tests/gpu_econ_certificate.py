@@ -40,7 +40,7 @@ def main():
             lens.psfnet.load_state_dict(sd)
         x = probes(n if ks < 20 else n // 8, 5)
         ref = lens.pred(x).double()
-        for mode in ("parity", "econ", "mixed", "fast"):
+        for mode in ("parity", "econ8", "econ", "mixed", "fast"):
             l1 = (lens.pred(x, mode=mode).double() - ref).abs().sum((-1, -2)) / 2
             q = torch.quantile(l1[:1 << 20].float(), torch.tensor([0.999, 0.9999], device="cuda"))
             print(f"[certificate] {name:24s} {mode:7s} probes={x.shape[0]} L1/2 max {float(l1.max()):.3e} "
