@@ -660,7 +660,7 @@ def test_econ8_mode_certified_between_parity_and_econ(pkg, lens):
     assert torch.equal(a, shallow.render_stack(noise, dep, foc, mode="parity"))
 
 
-@pytest.mark.parametrize("mode", ["parity", "econ", "fp32", "fast"])
+@pytest.mark.parametrize("mode", ["parity", "econ", "econ8", "fp32", "fast"])
 def test_c3_full_size_vs_reference_golden(lens, mode):
     """BASELINE config c3 (16 x 5 x 256 x 256, k = 11): all 16 images, all slices (1/64 of the pixels of every slice,
     1/4 of image 3, sums over everything); fp32 on images 0..3 only (16.5 Mpix/s kernel)."""
@@ -677,7 +677,7 @@ def test_c3_full_size_vs_reference_golden(lens, mode):
     if mode == "fast":
         assert float((out[..., ::8, ::8] - T(g["out_sub"])[:n]).abs().mean()) < 1e-4
         return
-    assert float((out.double().sum((1, 3, 4)) - T(g["sums"])[:n]).abs().max()) < 196608 * (1e-6 if mode == "econ" else 5e-7)
+    assert float((out.double().sum((1, 3, 4)) - T(g["sums"])[:n]).abs().max()) < 196608 * (1e-6 if mode.startswith("econ") else 5e-7)
 
 
 @pytest.fixture(scope="module")
@@ -692,7 +692,7 @@ def lens31_bench(pkg):
     return l
 
 
-@pytest.mark.parametrize("mode", ["parity", "econ", "fp32"])
+@pytest.mark.parametrize("mode", ["parity", "econ", "econ8", "fp32"])
 def test_c4_full_size_vs_reference_golden(lens31_bench, mode):
     """BASELINE config c4 (1 x 10 x 1080 x 1920, k = 31): the whole stack is rendered; the top-border, middle and
     bottom-border 8-row bands of slices 0, 5, 9 are compared with the reference's banded evaluation (its own
